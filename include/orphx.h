@@ -1,0 +1,188 @@
+/* orphx.h -- C ABI of liborphx.so: the B200-native flat-sky Fourier hot path that
+ * sits behind the orphics Python API (MapGen / FourierCalc / bin2D / qest).
+ *
+ * The reference (msyriac/orphics) is pure Python and has no FFI of its own: its
+ * hot path calls numpy and pixell.enmap directly.  The entry points below are
+ * therefore placed exactly at those call levels; each one names the reference
+ * interface (file:line under /root/reference/orphics/) it replaces.  The ctypes
+ * binding a maintainer would add is shown in INTEGRATION.md and lives in
+ * orphics_b200/_capi.py.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = OX_OK, negative = error; the
+ *     message of the last error on the calling thread is ox_last_error().
+ *   - plain pointers and sizes only.  `where` arguments say whether a data
+ *     pointer is host (OX_HOST) or device (OX_DEVICE) memory; host transfers are
+ *     done inside the call on the library stream.
+ *   - the caller owns every buffer it passes; handles own their device memory
+ *     and cuFFT plans.  Calls on one handle are not thread-safe.
+ *   - dtype: OX_F64 (double / double2) or OX_F32 (float / float2) arithmetic.
+ *   - maps are C-ordered [batch][ncomp][Ny][Nx]; "half-plane" Fourier arrays are
+ *     [batch][ncomp][Ny][Nx/2+1] complex (the r2c layout); "full-plane" Fourier
+ *     arrays are [batch][ncomp][Ny][Nx] complex (the layout numpy/pixell c2c
+ *     returns).
+ */
+#ifndef ORPHX_H
+#define ORPHX_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OX_ABI_VERSION 1
+
+enum { OX_OK = 0, OX_ERR_INVALID = -1, OX_ERR_CUDA = -2, OX_ERR_CUFFT = -3, OX_ERR_NOMEM = -4, OX_ERR_UNSUPPORTED = -5 };
+enum { OX_F64 = 0, OX_F32 = 1 };
+enum { OX_HOST = 0, OX_DEVICE = 1 };
+
+/* noise source of ox_sim_* (MapGen.get_map, maps.py:1577-1578) */
+enum {
+  OX_NOISE_HOST = 0,            /* caller uploads rand_gauss_harm's two standard_normal blocks: seed parity with numpy */
+  OX_NOISE_PHILOX = 1,          /* Philox4x32-10 + Box-Muller keyed by (seed, component, full-plane pixel): the reference algorithm, counter RNG */
+  OX_NOISE_PHILOX_HERMITIAN = 2 /* draws the Hermitian half-plane directly (half the normals); same statistics */
+};
+
+/* flag bits */
+enum {
+  OX_FLAG_ROT = 1,          /* QU<->EB rotation on the last two of 3 components (harm2map maps.py:1587 / iqu2teb maps.py:1614-1615) */
+  OX_FLAG_SKIP_CROSS = 2,   /* power2d(skip_cross=True) maps.py:1666 */
+  OX_FLAG_PIXEL_UNITS = 4,  /* f2power(pixel_units=True) maps.py:1622 */
+  OX_FLAG_IAU = 8,          /* iau sign convention of queb_rotmat (maps.py:1600,1607) */
+  OX_FLAG_MASK_NAN = 16,    /* bin2D.bin(mask_nan=True) stats.py:792-793 */
+  OX_FLAG_HARM = 32,        /* get_map(harm=True) maps.py:1581-1582 */
+  OX_FLAG_UNITARY = 64      /* enmap.fft(normalize=True): x Npix^-1/2 */
+};
+
+typedef struct ox_geometry ox_geometry;
+typedef struct ox_binner ox_binner;
+typedef struct ox_simplan ox_simplan;
+typedef struct ox_powerplan ox_powerplan;
+typedef struct ox_pipeline ox_pipeline;
+typedef struct ox_qeplan ox_qeplan;
+
+/* ---- runtime ------------------------------------------------------------- */
+int ox_abi_version(void);
+const char *ox_last_error(void);
+int ox_device_count(int *n);
+int ox_set_device(int dev);
+int ox_get_device(int *dev);
+int ox_device_name(char *buf, size_t len);
+int ox_synchronize(void);
+/* library stream: NULL (default) = the CUDA legacy default stream, which is also
+ * torch's default stream, so torch.distributed collectives order after our kernels. */
+int ox_set_stream(void *cuda_stream);
+int ox_malloc(void **dptr, size_t bytes);
+int ox_free(void *dptr);
+int ox_memset(void *dptr, int value, size_t bytes);
+int ox_host_alloc(void **hptr, size_t bytes); /* pinned */
+int ox_host_free(void *hptr);
+int ox_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int ox_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int ox_memcpy_d2d(void *dst, const void *src, size_t bytes);
+int ox_mem_info(size_t *free_bytes, size_t *total_bytes);
+/* device timers (CUDA events on the library stream) */
+int ox_timer_create(void **t);
+int ox_timer_start(void *t);
+int ox_timer_stop(void *t);
+int ox_timer_elapsed_ms(void *t, float *ms); /* synchronises on the stop event */
+int ox_timer_destroy(void *t);
+/* number of kernels / cuFFT executions this library has launched in this process */
+int ox_launch_count(long long *n);
+/* write `bytes` of zeros to a scratch buffer larger than L2 (bench hygiene) */
+int ox_flush_l2(void);
+
+/* ---- geometry: enmap.laxes / lmap / modlmap / area (maps.py:1374,1605,1607,1938-1939)
+ * ly[ny], lx[nx] are the caller's 2*pi*fftfreq axes (host); area in steradians.   */
+int ox_geometry_create(int ny, int nx, const double *ly, const double *lx, double area, ox_geometry **out);
+int ox_geometry_destroy(ox_geometry *g);
+/* modlmap = (ly^2+lx^2)^1/2, bit-identical to numpy's sum(lmap**2,0)**0.5 */
+int ox_geometry_modlmap(ox_geometry *g, double *out, int where);
+/* queb_rotmat (maps.py:1607): out[2][2][ny][nx] */
+int ox_geometry_rotmat(ox_geometry *g, int flags, double *out, int where);
+/* maps.mask_kspace (maps.py:1936-1948); NaN = "None" for the four cuts; out int32[ny][nx] */
+int ox_geometry_mask_kspace(ox_geometry *g, double lxcut, double lycut, double lmin, double lmax, int *out, int where);
+/* order-1 interpolation of tabulated spectra at modlmap, zero outside the table
+ * (the 2-D half of enmap.spec2flat, maps.py:1573): spec[nspec][nl] -> out[nspec][ny][nx] */
+int ox_geometry_interp_spec(ox_geometry *g, const double *spec, int nspec, int nl, double *out, int where);
+
+/* ---- stats.bin2D (stats.py:782-811) --------------------------------------- */
+/* bin2D.__init__ (stats.py:783-788): digitize(modrmap.ravel(), edges, right=True) */
+int ox_binner_create(const double *modrmap, int where, long long n, const double *edges, int nedges, ox_binner **out);
+/* same from a geometry's modlmap; additionally enables the fused half-plane path */
+int ox_binner_create_geom(ox_geometry *g, const double *edges, int nedges, ox_binner **out);
+int ox_binner_destroy(ox_binner *b);
+int ox_binner_digitized(ox_binner *b, long long *out_host);      /* int64[n], values 0..nedges */
+int ox_binner_counts(ox_binner *b, long long *out_host);         /* int64[nedges+1] = bincount(digitized, minlength=nedges+1) */
+/* bin2D.bin (stats.py:790-811), raw slot sums: for each of nmaps maps of n pixels
+ *   sums[m][s]   = sum_{digitized==s, kept} data*(weights or 1)
+ *   counts[m][s] = sum_{digitized==s, kept} (weights or 1)
+ * s = 0..nedges; the caller applies the reference's [1:-1] trim and the division. */
+int ox_binner_bin(ox_binner *b, const void *data, int dtype, int where, long long nmaps, const void *weights, int flags,
+                  double *sums, double *counts, int out_where);
+
+/* ---- maps.MapGen (maps.py:1553-1587) --------------------------------------- */
+/* covsqrt[ncomp][ncomp][ny][nx] float64 (what MapGen.__init__ stores, maps.py:1564-1573) */
+int ox_simplan_create(ox_geometry *g, int ncomp, const double *covsqrt, int where, int dtype, int max_batch, ox_simplan **out);
+int ox_simplan_destroy(ox_simplan *p);
+/* MapGen.get_map for nsim seeds.  noise (OX_NOISE_HOST only): float64
+ * [nsim][2][ncomp][ny][nx] = the real block then the imaginary block of
+ * rand_gauss_harm (maps.py:1578).  Output: real maps [nsim][ncomp][ny][nx] of
+ * `dtype`, or with OX_FLAG_HARM the full-plane complex covsqrt*rand (maps.py:1579-1582).
+ * OX_FLAG_ROT = harm2map's EB->QU rotation (scalar=False, ncomp==3). */
+int ox_sim_generate(ox_simplan *p, const long long *seeds, int nsim, int noise_mode, const double *noise, int noise_where,
+                    int flags, void *out, int out_where);
+
+/* ---- maps.FourierCalc (maps.py:1594-1677) ---------------------------------- */
+int ox_powerplan_create(ox_geometry *g, int ncomp, int dtype, int max_batch, ox_powerplan **out);
+int ox_powerplan_destroy(ox_powerplan *p);
+/* FourierCalc.iqu2teb / .fft (maps.py:1609-1617,1635-1636): real maps -> full-plane complex */
+int ox_power_fft(ox_powerplan *p, const void *maps, int where, int nbatch, int flags, void *kmap_out, int out_where);
+/* FourierCalc.ifft (maps.py:1632-1633): full-plane complex -> full-plane complex / Npix */
+int ox_power_ifft(ox_powerplan *p, const void *kmap, int where, int nbatch, void *out, int out_where);
+/* FourierCalc.f2power (maps.py:1620-1624) on n complex elements */
+int ox_power_f2power(ox_powerplan *p, const void *k1, const void *k2, int where, long long n, int flags, void *out, int out_where);
+/* FourierCalc.power2d (maps.py:1639-1677): p2d[nbatch][ncomp][ncomp][ny][nx] real,
+ * optional full-plane kmaps.  maps2 may be NULL (auto). */
+int ox_power2d(ox_powerplan *p, const void *maps1, const void *maps2, int where, int nbatch, int flags, void *p2d_out,
+               void *kmap1_out, void *kmap2_out, int out_where);
+/* fused power2d + bin2D.bin (maps.binned_power, maps.py:1350-1361) without
+ * materialising p2d: bandpowers[nbatch][nspec][nedges-1] float64, nspec =
+ * ncomp(ncomp+1)/2 ordered (0,0),(0,1)..(0,n-1),(1,1).. ; window (may be NULL) is a
+ * real [ny][nx] taper multiplied into the maps first. The binner must come from
+ * ox_binner_create_geom. */
+int ox_power_bin(ox_powerplan *p, ox_binner *b, const void *maps1, const void *maps2, int where, int nbatch, int flags,
+                 const void *window, int window_where, double *bandpowers, int out_where);
+
+/* ---- fused sim -> FFT -> power2d -> bin2D pipeline (north-star path) -------- */
+int ox_pipeline_create(ox_simplan *s, ox_powerplan *p, ox_binner *b, const double *window, int window_where, ox_pipeline **out);
+int ox_pipeline_destroy(ox_pipeline *pl);
+/* bandpowers[nsim][nspec][nbins]; also accumulates the Statistics triple
+ * (stats.py:1085-1090): N += nsim, SUM += x, CROSS += x x^T with x = the
+ * flattened [nspec*nbins] bandpower vector of each sim. */
+int ox_pipeline_run(ox_pipeline *pl, const long long *seeds, int nsim, int noise_mode, const double *noise, int noise_where,
+                    int flags, double *bandpowers, int out_where);
+/* one ox_pipeline_run with CUDA events between the stages; stage_ms[6] = sim_fill, cuFFT
+ * inverse, window, cuFFT forward, power_bin (+finalize), statistics.  Philox modes only. */
+int ox_pipeline_profile(ox_pipeline *pl, const long long *seeds, int nsim, int noise_mode, int flags, float *stage_ms);
+/* device pointers of the accumulators (for a torch.distributed / NCCL all-reduce in place) */
+int ox_pipeline_stats(ox_pipeline *pl, long long **n_dev, double **sum_dev, double **cross_dev, int *dim);
+int ox_pipeline_stats_reset(ox_pipeline *pl);
+
+/* ---- lensing.qest (tutorials/tt_verification.ipynb:81,608,610; lensing.py:973-976) */
+enum { OX_QE_TT = 0, OX_QE_EB = 1 };
+/* filters are full-plane [ny][nx] float64: wxy = W_XY, wy = W_Y, norm = A_L-multiplier*kmask_K */
+int ox_qeplan_create(ox_geometry *g, int est, const double *wxy, const double *wy, const double *norm, int where, int dtype,
+                     int max_batch, ox_qeplan **out);
+int ox_qeplan_destroy(ox_qeplan *q);
+/* kappa_from_map: inputs are real maps [nbatch][ny][nx] (X leg; Y leg may be NULL = same) or with
+ * alreadyFTed full-plane complex; output real kappa map or (returnFt) full-plane complex kappa(l).
+ * meanfield_accum (device, may be NULL): complex full-plane accumulator += kappa(l), count += nbatch */
+int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int nbatch, int already_ft, int return_ft,
+                      void *kappa_out, int out_where);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORPHX_H */

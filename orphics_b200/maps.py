@@ -1,0 +1,556 @@
+"""orphics.maps hot-path mirror on B200: MapGen (maps.py:1553-1587), FourierCalc
+(maps.py:1594-1677) and the helpers around them (rect_geometry :1472, binned_power
+:1350, get_taper/cosine_window :1873-1920, filter_map :1922, gauss_beam :1925,
+mask_kspace :1936), with the reference's names, arguments and return conventions.
+All per-pixel arithmetic runs in liborphx.so (CUDA, sm_100a); there is no CPU
+fallback.  Batched entry points (get_maps, power2d_batch, binned_power_batch,
+SimPipeline) are additions: the reference treats a leading axis as polarisation
+components, never as a batch (maps.py:1648,1661).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi, enmap
+from ._capi import lib, check, ptr, OX_HOST, OX_DEVICE
+from .enmap import Geometry, ndmap
+
+
+# --------------------------------------------------------------------------- geometry
+def rect_geometry(width_arcmin=None, width_deg=None, px_res_arcmin=0.5, proj="car", pol=False,
+                  height_deg=None, height_arcmin=None, xoffset_degree=0., yoffset_degree=0., extra=False, **kwargs):
+    """Shape and wcs of a rectangular patch centred on the given offsets (maps.py:1472-1498)."""
+    if width_deg is not None:
+        width_arcmin = 60. * width_deg
+    if height_deg is not None:
+        height_arcmin = 60. * height_deg
+    hwidth = width_arcmin / 2.
+    vwidth = hwidth if height_arcmin is None else height_arcmin / 2.
+    arcmin, degree = enmap.arcmin, enmap.degree
+    lo = [-vwidth * arcmin + yoffset_degree * degree, -hwidth * arcmin + xoffset_degree * degree]
+    hi = [vwidth * arcmin + yoffset_degree * degree, hwidth * arcmin + xoffset_degree * degree]
+    shape, wcs = enmap.geometry(pos=[lo, hi], res=px_res_arcmin * arcmin, proj=proj, **kwargs)
+    if pol:
+        shape = (3,) + shape
+    if extra:
+        modlmap = enmap.modlmap(shape, wcs)
+        ells = np.arange(0, modlmap.max(), 1.)
+        return shape, wcs, modlmap, ells
+    return shape, wcs
+
+
+def _ncomp(shape):
+    return int(shape[-3]) if len(shape) > 2 else 1
+
+
+# --------------------------------------------------------------------------- spec2flat
+def _eigpow(A, e):
+    """Symmetric matrix power along axes [0,1] of (n,n,...) (pixell utils.eigpow as used by
+    enmap.multi_pow, maps.py:1571): negative / relatively tiny eigenvalues -> 0 for
+    non-integer or negative exponents."""
+    A = np.asarray(A, dtype=np.float64)
+    if A.shape[0] == 1:
+        a = A[0, 0]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.where(a > 0, np.abs(a) ** e, 0.0)[None, None]
+    M = np.moveaxis(A, (0, 1), (-2, -1))
+    E, V = np.linalg.eigh(M)
+    emax = np.max(np.abs(E), -1, keepdims=True)
+    bad = (E < emax * np.finfo(np.float64).resolution * 100) | (E < np.finfo(np.float64).tiny * 1e4)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        Ee = np.where(bad, 0.0, np.abs(E) ** e)
+    return np.moveaxis(np.einsum("...ik,...k,...jk->...ij", V, Ee, V), (-2, -1), (0, 1))
+
+
+def _sym_convolve(a, b):
+    sa = np.concatenate([a, a[:, -2:0:-1]], -1)
+    sb = np.concatenate([b, b[:, -2:0:-1]], -1)
+    out = np.fft.irfft(np.fft.rfft(sa, axis=-1) * np.fft.rfft(sb, axis=-1), n=sa.shape[-1], axis=-1)
+    return out[:, :a.shape[-1]]
+
+
+def smooth_spectrum(ps, width):
+    """Mode-weighted Gaussian smoothing along l (enmap.smooth_spectrum, kernel='gauss', weight='mode')."""
+    ps = np.asarray(ps, dtype=np.float64)
+    flat = ps.reshape(-1, ps.shape[-1])
+    l = np.arange(flat.shape[-1], dtype=np.float64)
+    K = np.tile(np.exp(-0.5 * (l / width) ** 2), (flat.shape[0], 1))
+    W = np.tile(l ** 2, (flat.shape[0], 1))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        res = _sym_convolve(flat * W, K) / _sym_convolve(W, K)
+    return res.reshape(ps.shape)
+
+
+def spec2flat(shape, wcs, cov, exp=1.0, mode="constant", smooth="auto", method=None):
+    """enmap.spec2flat as MapGen calls it (maps.py:1573): (ncomp,ncomp,nl) -> (ncomp,ncomp,Ny,Nx).
+    The short 1-D treatment (smoothing, x Npix/area, matrix power) is host set-up; the
+    per-pixel order-1 interpolation at |l| runs on the device."""
+    if mode != "constant":
+        raise NotImplementedError("only mode='constant'")
+    g = Geometry.get(shape, wcs, method)
+    cov = np.array(cov, dtype=np.float64)
+    if cov.ndim == 1:
+        cov = cov[None, None]
+    if smooth == "auto":
+        smooth = 0.5 * (abs(g.ly[1]) + abs(g.lx[1])) / 3.41
+    if smooth and smooth > 0:
+        cov = smooth_spectrum(cov, smooth)
+    cov = cov * g.npix / g.area
+    if exp != 1.0:
+        cov = _eigpow(cov, exp)
+    cov[~np.isfinite(cov)] = 0
+    return ndmap(g.interp_spec(cov), wcs)
+
+
+def spec1d_to_2d(shape, wcs, ps):
+    """maps.py:1591-1592."""
+    return spec2flat(shape, wcs, ps) / (np.prod(shape[-2:]) / enmap.area(shape, wcs))
+
+
+# --------------------------------------------------------------------------- MapGen
+class MapGen(object):
+    """Pre-computes covsqrt for a geometry, then draws Gaussian random fields
+    (maps.py:1553-1587).
+
+    noise: "numpy" (default) draws the white noise with numpy's global legacy RNG exactly as
+    the reference does (np.random.seed(seed); rand_gauss_harm) and uploads it, so maps agree
+    with the reference for identical seeds; "philox" / "philox_hermitian" draw on the
+    device (throughput modes, see include/orphx.h).
+    dtype: np.float64 (default) or np.float32 arithmetic."""
+
+    def __init__(self, shape, wcs, cov=None, covsqrt=None, pixel_units=False, smooth="auto", ndown=None, order=1,
+                 noise="numpy", dtype=np.float64, max_batch=1, method=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.wcs = wcs
+        self.geometry = Geometry.get(shape, wcs, method)
+        if covsqrt is not None:
+            self.covsqrt = covsqrt
+        else:
+            assert cov.ndim >= 3, "Power spectra have to be of shape (ncomp,ncomp,lmax) or (ncomp,ncomp,Ny,Nx)."
+            if cov.ndim == 4:
+                if not (pixel_units):
+                    cov = cov * np.prod(shape[-2:]) / self.geometry.area
+                if ndown:
+                    raise NotImplementedError("ndown (downsample_power) is outside the accelerated path")
+                self.covsqrt = ndmap(_eigpow(cov, 0.5), wcs)
+            else:
+                self.covsqrt = spec2flat(shape, wcs, cov, 0.5, mode="constant", smooth=smooth, method=method)
+        cs = np.asarray(self.covsqrt, dtype=np.float64)
+        if cs.ndim == 2:
+            cs = cs[None, None]
+        self.ncomp = cs.shape[0]
+        if cs.shape[:2] != (self.ncomp, self.ncomp) or cs.shape[-2:] != self.geometry.shape:
+            raise ValueError(f"covsqrt shape {cs.shape} does not match geometry {self.shape}")
+        if _ncomp(self.shape) != self.ncomp:
+            raise ValueError(f"shape {self.shape} has {_ncomp(self.shape)} components but covsqrt has {self.ncomp}")
+        self.noise = noise
+        self.dtype = _capi.ox_dtype(dtype)
+        self.max_batch = int(max_batch)
+        h = C.c_void_p()
+        cs = np.ascontiguousarray(cs)
+        check(lib.ox_simplan_create(self.geometry.handle, self.ncomp, ptr(cs), OX_HOST, self.dtype, self.max_batch, C.byref(h)))
+        self.handle = h
+
+    # -- noise exactly as the reference draws it (maps.py:1577-1578)
+    def _numpy_noise(self, seed, out=None):
+        if seed is not None:
+            np.random.seed(seed)
+        shp = self.shape if len(self.shape) > 2 else self.shape[-2:]
+        if out is None:
+            out = np.empty((2,) + (self.ncomp,) + self.geometry.shape, dtype=np.float64)
+        out[0] = np.random.standard_normal(shp).reshape((self.ncomp,) + self.geometry.shape)
+        out[1] = np.random.standard_normal(shp).reshape((self.ncomp,) + self.geometry.shape)
+        return out
+
+    def _generate(self, seeds, flags, noise_mode=None, noise_arrays=None):
+        mode = _capi.NOISE_MODES[noise_mode or self.noise]
+        nsim = len(seeds)
+        if nsim > self.max_batch:
+            raise ValueError(f"{nsim} sims requested but max_batch={self.max_batch}")
+        noise = None
+        seeds64 = np.ascontiguousarray([0 if s is None else s for s in seeds], dtype=np.int64)
+        if mode == _capi.NOISE_HOST:
+            if noise_arrays is not None:
+                noise = np.ascontiguousarray(noise_arrays, dtype=np.float64)
+            else:
+                noise = np.empty((nsim, 2, self.ncomp) + self.geometry.shape, dtype=np.float64)
+                for i, s in enumerate(seeds):
+                    self._numpy_noise(s, noise[i])
+        rdt, cdt = _capi.np_dtype(self.dtype), _capi.np_cdtype(self.dtype)
+        if flags & _capi.FLAG_HARM:
+            out = np.empty((nsim, self.ncomp) + self.geometry.shape, dtype=cdt)
+        else:
+            out = np.empty((nsim, self.ncomp) + self.geometry.shape, dtype=rdt)
+        check(lib.ox_sim_generate(self.handle, ptr(seeds64), nsim, mode, ptr(noise), OX_HOST, flags, ptr(out), OX_HOST))
+        return out
+
+    def _flags(self, scalar, iau, harm):
+        flags = 0
+        if harm:
+            flags |= _capi.FLAG_HARM
+        elif not scalar and self.ncomp > 1:
+            if self.ncomp != 3:
+                raise NotImplementedError("EB->QU rotation (scalar=False) needs ncomp == 3; pass scalar=True")
+            flags |= _capi.FLAG_ROT
+        if iau:
+            flags |= _capi.FLAG_IAU
+        return flags
+
+    def get_map(self, seed=None, scalar=False, iau=False, real=False, harm=False):
+        """maps.py:1576-1587."""
+        if real:
+            raise NotImplementedError("real=True (white noise drawn in real space) is outside the accelerated path")
+        out = self._generate([seed], self._flags(scalar, iau, harm))[0]
+        if len(self.shape) == 2:
+            out = out[0]
+        return ndmap(out, self.wcs)
+
+    def get_maps(self, seeds, scalar=False, iau=False, harm=False, noise=None):
+        """Batched get_map: (nsim,[ncomp,]Ny,Nx)."""
+        out = self._generate(list(seeds), self._flags(scalar, iau, harm), noise_mode=noise)
+        if len(self.shape) == 2:
+            out = out[:, 0]
+        return ndmap(out, self.wcs)
+
+    def __del__(self):
+        try:
+            lib.ox_simplan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------- FourierCalc
+class FourierCalc(object):
+    """Pre-computes what Fourier transforms and power spectra of a geometry need
+    (maps.py:1594-1677)."""
+
+    def __init__(self, shape, wcs, iau=False, dtype=np.float64, max_batch=1, method=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.wcs = wcs
+        self.iau = iau
+        self.geometry = Geometry.get(shape, wcs, method)
+        self.normfact = self.geometry.area / (np.prod(self.shape[-2:]) ** 2.)
+        self.ncomp = _ncomp(self.shape)
+        if self.ncomp > 3:
+            raise NotImplementedError("FourierCalc supports up to 3 components")
+        self.dtype = _capi.ox_dtype(dtype)
+        self.max_batch = int(max_batch)
+        self._rot = None
+        self._plans = {}
+        self._retired = []
+
+    @property
+    def rot(self):
+        """queb_rotmat(lmap) (maps.py:1607), built on the device on first use."""
+        if self._rot is None and len(self.shape) > 2 and self.shape[-3] > 1:
+            self._rot = ndmap(self.geometry.rotmat(self.iau), self.wcs)
+        return self._rot
+
+    def _plan(self, ncomp, nbatch=1):
+        nb = max(self.max_batch, nbatch)
+        key = ncomp
+        if key in self._plans and self._plans[key][1] >= nb:
+            return self._plans[key][0]
+        if key in self._plans:
+            self._retired.append(self._plans[key][0])  # may still be referenced by a SimPipeline
+        h = C.c_void_p()
+        check(lib.ox_powerplan_create(self.geometry.handle, ncomp, self.dtype, nb, C.byref(h)))
+        self._plans[key] = (h, nb)
+        return h
+
+    def _as_stack(self, emap):
+        a = np.asarray(emap)
+        if np.iscomplexobj(a):
+            raise NotImplementedError("FourierCalc transforms real maps; complex input is outside the accelerated path")
+        if a.shape[-2:] != self.geometry.shape:
+            raise ValueError(f"map shape {a.shape} does not match geometry {self.geometry.shape}")
+        nc = a.shape[-3] if a.ndim > 2 else 1
+        return np.ascontiguousarray(a, dtype=_capi.np_dtype(self.dtype)).reshape((1, nc) + self.geometry.shape), nc
+
+    def _flags(self, rot=True, pixel_units=False, skip_cross=False, normalize=False):
+        f = 0
+        if rot:
+            f |= _capi.FLAG_ROT
+        if pixel_units:
+            f |= _capi.FLAG_PIXEL_UNITS
+        if skip_cross:
+            f |= _capi.FLAG_SKIP_CROSS
+        if self.iau:
+            f |= _capi.FLAG_IAU
+        if normalize:
+            f |= _capi.FLAG_UNITARY
+        return f
+
+    def iqu2teb(self, emap, nthread=0, normalize=True, rot=True):
+        """2-D FFT of the map(s) with the QU->EB rotation (maps.py:1609-1617). nthread is ignored."""
+        if normalize not in (True, False):
+            raise NotImplementedError("normalize='phys' is outside the accelerated path")
+        stack, nc = self._as_stack(emap)
+        out = np.empty(stack.shape, dtype=_capi.np_cdtype(self.dtype))
+        flags = self._flags(rot=rot and nc == 3, normalize=bool(normalize))
+        check(lib.ox_power_fft(self._plan(nc), ptr(stack), OX_HOST, 1, flags, ptr(out), OX_HOST))
+        return ndmap(out.reshape(np.shape(emap)), self.wcs)
+
+    def f2power(self, kmap1, kmap2, pixel_units=False):
+        """Re(conj(k1) k2) * normfact for already transformed maps (maps.py:1620-1624)."""
+        cdt = _capi.np_cdtype(self.dtype)
+        k1 = np.ascontiguousarray(kmap1, dtype=cdt)
+        k2 = k1 if kmap2 is kmap1 else np.ascontiguousarray(kmap2, dtype=cdt)
+        if k1.shape != k2.shape:
+            raise ValueError("kmap shapes differ")
+        out = np.empty(k1.shape, dtype=_capi.np_dtype(self.dtype))
+        check(lib.ox_power_f2power(self._plan(1), ptr(k1), ptr(k2), OX_HOST, k1.size, self._flags(rot=False, pixel_units=pixel_units), ptr(out), OX_HOST))
+        return out
+
+    def f1power(self, map1, kmap2, pixel_units=False, nthread=0):
+        """maps.py:1626-1630."""
+        kmap1 = self.iqu2teb(map1, nthread, normalize=False)
+        return self.f2power(kmap1, kmap2, pixel_units), kmap1
+
+    def ifft(self, kmap):
+        """Backward c2c / Npix (maps.py:1632-1633)."""
+        cdt = _capi.np_cdtype(self.dtype)
+        k = np.ascontiguousarray(kmap, dtype=cdt)
+        nc = k.shape[-3] if k.ndim > 2 else 1
+        out = np.empty(k.shape, dtype=cdt)
+        check(lib.ox_power_ifft(self._plan(nc), ptr(k), OX_HOST, 1, ptr(out), OX_HOST))
+        return ndmap(out, self.wcs)
+
+    def fft(self, emap):
+        """Raw forward FFT, no rotation (maps.py:1635-1636)."""
+        return self.iqu2teb(emap, normalize=False, rot=False)
+
+    def power2d(self, emap=None, emap2=None, nthread=0, pixel_units=False, skip_cross=False, rot=True, kmap=None,
+                kmap2=None, dtype=None):
+        """Power spectrum of emap crossed with emap2 (= emap if None); radians^2 unless
+        pixel_units (maps.py:1639-1677)."""
+        wcs = getattr(emap, "wcs", None) if emap is not None else getattr(kmap, "wcs", None)
+        wcs = self.wcs if wcs is None else wcs
+        if kmap is not None or kmap2 is not None:
+            # already-transformed inputs: spectra from f2power, as the reference does
+            lteb1 = kmap if kmap is not None else self.iqu2teb(emap, nthread, normalize=False, rot=rot)
+            lteb2 = kmap2 if kmap2 is not None else (self.iqu2teb(emap2, nthread, normalize=False, rot=rot) if emap2 is not None else lteb1)
+            assert np.shape(lteb1) == np.shape(lteb2)
+            ndim = np.ndim(lteb1)
+            ncomp = np.shape(lteb1)[-3] if ndim > 2 else 1
+            if ndim > 2 and ncomp > 1:
+                retpow = np.zeros((ncomp, ncomp) + np.shape(lteb1)[-2:], dtype=dtype)
+                for i in range(ncomp):
+                    retpow[i, i] = self.f2power(lteb1[i], lteb2[i], pixel_units)
+                if not (skip_cross):
+                    for i in range(ncomp):
+                        for j in range(i + 1, ncomp):
+                            retpow[i, j] = self.f2power(lteb1[i], lteb2[j], pixel_units)
+                            retpow[j, i] = retpow[i, j]
+                return retpow, lteb1, lteb2
+            if ndim > 2:
+                lteb1, lteb2 = lteb1[0], lteb2[0]
+            return ndmap(self.f2power(lteb1, lteb2, pixel_units), wcs), ndmap(lteb1, wcs), ndmap(lteb2, wcs)
+        s1, nc = self._as_stack(emap)
+        s2 = None
+        if emap2 is not None:
+            s2, nc2 = self._as_stack(emap2)
+            assert s1.shape == s2.shape
+        rdt, cdt = _capi.np_dtype(self.dtype), _capi.np_cdtype(self.dtype)
+        p2d = np.empty((nc, nc) + self.geometry.shape, dtype=rdt)
+        k1 = np.empty(s1.shape, dtype=cdt)
+        k2 = np.empty(s1.shape, dtype=cdt) if s2 is not None else None
+        flags = self._flags(rot=rot and nc == 3, pixel_units=pixel_units, skip_cross=skip_cross)
+        check(lib.ox_power2d(self._plan(nc), ptr(s1), ptr(s2), OX_HOST, 1, flags, ptr(p2d), ptr(k1), ptr(k2), OX_HOST))
+        if k2 is None:
+            k2 = k1
+        if np.ndim(emap) > 2 and nc > 1:
+            ret = p2d if dtype is None else p2d.astype(dtype)
+            return ret, ndmap(k1[0], wcs), ndmap(k2[0], wcs)
+        return ndmap(p2d[0, 0], wcs), ndmap(k1[0, 0], wcs), ndmap(k2[0, 0], wcs)
+
+    # ---- batched / fused additions
+    def binned_power_batch(self, binner, maps, maps2=None, window=None, pixel_units=False, skip_cross=False, rot=True):
+        """power2d + bin2D.bin for a stack (nbatch,[ncomp,]Ny,Nx) without materialising p2d;
+        returns bandpowers (nbatch, nspec, nbins), nspec ordered (0,0),(0,1)..,(1,1),.. .
+        ``binner`` must be a stats.bin2D built with geometry=."""
+        a = np.asarray(maps)
+        nc = self.ncomp
+        rdt = _capi.np_dtype(self.dtype)
+        s1 = np.ascontiguousarray(a, dtype=rdt).reshape((-1, nc) + self.geometry.shape)
+        nb = s1.shape[0]
+        s2 = None
+        if maps2 is not None:
+            s2 = np.ascontiguousarray(maps2, dtype=rdt).reshape(s1.shape)
+        w = None if window is None else np.ascontiguousarray(window, dtype=rdt)
+        ns = nc if (skip_cross and nc > 1) else nc * (nc + 1) // 2
+        out = np.empty((nb, ns, binner.centers.size), dtype=np.float64)
+        flags = self._flags(rot=rot and nc == 3, pixel_units=pixel_units, skip_cross=skip_cross)
+        check(lib.ox_power_bin(self._plan(nc, nb), binner.handle, ptr(s1), ptr(s2), OX_HOST, nb, flags, ptr(w), OX_HOST, ptr(out), OX_HOST))
+        return out
+
+    def __del__(self):
+        try:
+            for h, _ in self._plans.values():
+                lib.ox_powerplan_destroy(h)
+            for h in self._retired:
+                lib.ox_powerplan_destroy(h)
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------- helpers
+def binned_power(imap, bin_edges=None, binner=None, fc=None, modlmap=None, imap2=None, mask=1):
+    """Binned power spectrum of a map in one line (maps.py:1350-1361)."""
+    from . import stats
+    shape, wcs = imap.shape, imap.wcs
+    fc = FourierCalc(shape, wcs) if fc is None else fc
+    if binner is None:
+        if modlmap is None:
+            binner = stats.bin2D(fc.geometry.modlmap(), bin_edges, geometry=fc.geometry)
+        else:
+            binner = stats.bin2D(modlmap, bin_edges)
+    if getattr(binner, "geometry", None) is fc.geometry and np.ndim(imap) == 2:
+        w = None if np.isscalar(mask) and mask == 1 else np.broadcast_to(np.asarray(mask, dtype=np.float64), fc.geometry.shape)
+        p1d = fc.binned_power_batch(binner, imap, imap2, window=w)[0, 0]
+        return binner.centers, p1d / np.mean(np.asarray(mask, dtype=np.float64) ** 2.)
+    p2d, _, _ = fc.power2d(imap * mask, imap2 * mask if imap2 is not None else None)
+    cents, p1d = binner.bin(p2d)
+    return cents, p1d / np.mean(mask ** 2.)
+
+
+def cosine_window(Ny, Nx, lenApodY=30, lenApodX=30, padY=0, padX=0):
+    """Separable raised-cosine apodisation with zero padding (maps.py:1893-1920)."""
+    def edge_profile(n, lap, pad):
+        prof = np.ones(n)
+        if lap > 0:
+            idx = np.arange(n)
+            lo = idx <= (lap + pad)
+            prof[lo] = 1. / 2 * (1 - np.cos(-np.pi * (idx[lo].astype(float) - pad) / lap))
+            hi = idx >= ((n - 1) - lap - pad)
+            prof[hi] = 1. / 2 * (1 - np.cos(-np.pi * ((n - 1) - idx[hi] - pad).astype(float) / lap))
+        return prof
+    win = np.ones((Ny, Nx)) * edge_profile(Nx, lenApodX, padX)[None, :]
+    win = win * edge_profile(Ny, lenApodY, padY)[:, None]
+    win[0:padY, :] = 0
+    win[:, 0:padX] = 0
+    win[Ny - padY:, :] = 0
+    win[:, Nx - padX:] = 0
+    return win
+
+
+def get_taper(shape, wcs, taper_percent=12.0, pad_percent=3.0, weight=None):
+    """maps.py:1873-1879."""
+    Ny, Nx = shape[-2:]
+    if weight is None:
+        weight = np.ones(shape[-2:])
+    apod = int(taper_percent * min(Ny, Nx) / 100.)
+    pad = int(pad_percent * min(Ny, Nx) / 100.)
+    taper = cosine_window(Ny, Nx, lenApodY=apod, lenApodX=apod, padY=pad, padX=pad) * weight
+    w2 = np.mean(taper ** 2.)
+    return ndmap(taper, wcs), w2
+
+
+def gauss_beam(ell, fwhm):
+    """maps.py:1925-1927 (fwhm in arcmin)."""
+    tht_fwhm = np.deg2rad(fwhm / 60.)
+    return np.exp(-(tht_fwhm ** 2.) * (ell ** 2.) / (16. * np.log(2.)))
+
+
+def mask_kspace(shape, wcs, lxcut=None, lycut=None, lmin=None, lmax=None, method=None):
+    """Integer l-space mask, computed on the device (maps.py:1936-1948)."""
+    g = Geometry.get(shape, wcs, method)
+    return ndmap(g.mask_kspace(lxcut, lycut, lmin, lmax).astype(int), wcs)
+
+
+def filter_map(imap, kfilter, fc=None):
+    """Re(ifft(fft(imap) * kfilter)) / Npix (maps.py:1922-1923)."""
+    fc = FourierCalc(imap.shape, imap.wcs) if fc is None else fc
+    k = fc.fft(imap)
+    return ndmap(np.real(fc.ifft(np.asarray(k) * kfilter)), imap.wcs)
+
+
+# --------------------------------------------------------------------------- fused pipeline
+class SimPipeline(object):
+    """sim -> FFT -> power2d -> bin2D for batches of seeds in one device-resident pass
+    (ox_pipeline_*): MapGen.get_map, an optional real-space taper, FourierCalc.power2d and
+    bin2D.bin, plus the Statistics triple of the bandpower vectors accumulated on the
+    device.  Bandpowers come back as (nsim, nspec, nbins)."""
+
+    def __init__(self, mapgen, fc, binner, window=None):
+        if binner.geometry is None:
+            raise ValueError("SimPipeline needs a bin2D built with geometry=")
+        self.mapgen, self.fc, self.binner = mapgen, fc, binner
+        self.window = None if window is None else np.ascontiguousarray(window, dtype=np.float64)
+        self._pplan = fc._plan(mapgen.ncomp, mapgen.max_batch)
+        h = C.c_void_p()
+        check(lib.ox_pipeline_create(mapgen.handle, self._pplan, binner.handle, ptr(self.window), OX_HOST, C.byref(h)))
+        self.handle = h
+        self.nspec = mapgen.ncomp * (mapgen.ncomp + 1) // 2
+        self.nbins = binner.centers.size
+        self.dim = self.nspec * self.nbins
+
+    def _flags(self, scalar, iau):
+        f = 0
+        if not scalar and self.mapgen.ncomp == 3:
+            f |= _capi.FLAG_ROT
+        if iau:
+            f |= _capi.FLAG_IAU
+        return f
+
+    def run(self, seeds, scalar=False, iau=False, noise=None, out=None, fetch=True):
+        """Bandpowers of len(seeds) sims.  noise: None -> the MapGen's mode."""
+        mg = self.mapgen
+        mode = _capi.NOISE_MODES[noise or mg.noise]
+        seeds = list(seeds)
+        nsim = len(seeds)
+        res = np.empty((nsim, self.nspec, self.nbins), dtype=np.float64) if out is None else out
+        flags = self._flags(scalar, iau)
+        done = 0
+        while done < nsim:
+            n = min(mg.max_batch, nsim - done)
+            chunk = seeds[done:done + n]
+            s64 = np.ascontiguousarray(chunk, dtype=np.int64)
+            nz = None
+            if mode == _capi.NOISE_HOST:
+                nz = np.empty((n, 2, mg.ncomp) + mg.geometry.shape, dtype=np.float64)
+                for i, s in enumerate(chunk):
+                    mg._numpy_noise(s, nz[i])
+            dst = res[done:done + n]
+            check(lib.ox_pipeline_run(self.handle, ptr(s64), n, mode, ptr(nz), OX_HOST, flags,
+                                      ptr(dst) if fetch else None, OX_HOST))
+            done += n
+        return res if fetch else None
+
+    def run_raw(self, seeds_i64, nsim, mode, flags, out_ptr):
+        """Thin call for benchmarks: seeds_i64 is a contiguous int64 numpy array (e.g. pinned)."""
+        check(lib.ox_pipeline_run(self.handle, ptr(seeds_i64), nsim, mode, None, OX_HOST, flags, out_ptr, OX_HOST))
+
+    STAGES = ("sim_fill", "cufft_inverse", "window", "cufft_forward", "power_bin", "statistics")
+
+    def profile(self, seeds_i64, nsim, mode, flags):
+        """Per-stage device times (ms) of one run, from CUDA events between the stages."""
+        ms = (C.c_float * 6)()
+        check(lib.ox_pipeline_profile(self.handle, ptr(seeds_i64), nsim, mode, flags, ms))
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
+
+    def stats_pointers(self):
+        n, s, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        d = C.c_int()
+        check(lib.ox_pipeline_stats(self.handle, C.byref(n), C.byref(s), C.byref(c), C.byref(d)))
+        return n.value, s.value, c.value, d.value
+
+    def stats(self):
+        """(N, SUM, CROSS) accumulated on the device so far."""
+        n, s, c, d = self.stats_pointers()
+        N = np.empty(1, dtype=np.int64)
+        S = np.empty(d, dtype=np.float64)
+        Cm = np.empty((d, d), dtype=np.float64)
+        check(lib.ox_memcpy_d2h(ptr(N), C.c_void_p(n), 8))
+        check(lib.ox_memcpy_d2h(ptr(S), C.c_void_p(s), 8 * d))
+        check(lib.ox_memcpy_d2h(ptr(Cm), C.c_void_p(c), 8 * d * d))
+        return int(N[0]), S, Cm
+
+    def reset_stats(self):
+        check(lib.ox_pipeline_stats_reset(self.handle))
+
+    def __del__(self):
+        try:
+            lib.ox_pipeline_destroy(self.handle)
+        except Exception:
+            pass
