@@ -52,7 +52,8 @@ enum {
   OX_FLAG_IAU = 8,          /* iau sign convention of queb_rotmat (maps.py:1600,1607) */
   OX_FLAG_MASK_NAN = 16,    /* bin2D.bin(mask_nan=True) stats.py:792-793 */
   OX_FLAG_HARM = 32,        /* get_map(harm=True) maps.py:1581-1582 */
-  OX_FLAG_UNITARY = 64      /* enmap.fft(normalize=True): x Npix^-1/2 */
+  OX_FLAG_UNITARY = 64,     /* enmap.fft(normalize=True): x Npix^-1/2 */
+  OX_FLAG_KEEP_MAPS = 128   /* ox_pipeline_run: also store the real-space maps (before the taper) in HBM */
 };
 
 typedef struct ox_geometry ox_geometry;
@@ -163,6 +164,12 @@ int ox_pipeline_destroy(ox_pipeline *pl);
  * flattened [nspec*nbins] bandpower vector of each sim. */
 int ox_pipeline_run(ox_pipeline *pl, const long long *seeds, int nsim, int noise_mode, const double *noise, int noise_where,
                     int flags, double *bandpowers, int out_where);
+/* which implementation the pipeline uses: 1 = cuFFT passes + hand-written kernels around them,
+ * 2 = fused hand-written FFT kernels (power-of-two maps; ORPHX_PIPELINE=cufft|fused overrides) */
+int ox_pipeline_path(ox_pipeline *pl, int *path);
+/* device pointer of the real maps [max_batch][ncomp][ny][nx] of the last run (path 1: always;
+ * path 2: when OX_FLAG_KEEP_MAPS was given) */
+int ox_pipeline_maps(ox_pipeline *pl, void **maps_dev);
 /* one ox_pipeline_run with CUDA events between the stages; stage_ms[6] = sim_fill, cuFFT
  * inverse, window, cuFFT forward, power_bin (+finalize), statistics.  Philox modes only. */
 int ox_pipeline_profile(ox_pipeline *pl, const long long *seeds, int nsim, int noise_mode, int flags, float *stage_ms);

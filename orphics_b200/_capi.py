@@ -16,6 +16,7 @@ OX_F64, OX_F32 = 0, 1
 OX_HOST, OX_DEVICE = 0, 1
 NOISE_HOST, NOISE_PHILOX, NOISE_PHILOX_HERMITIAN = 0, 1, 2
 FLAG_ROT, FLAG_SKIP_CROSS, FLAG_PIXEL_UNITS, FLAG_IAU, FLAG_MASK_NAN, FLAG_HARM, FLAG_UNITARY = 1, 2, 4, 8, 16, 32, 64
+FLAG_KEEP_MAPS = 128
 QE_TT, QE_EB = 0, 1
 
 NOISE_MODES = {"host": NOISE_HOST, "numpy": NOISE_HOST, "philox": NOISE_PHILOX,
@@ -91,6 +92,8 @@ SIGNATURES = {
     "ox_pipeline_create": [_vp, _vp, _vp, _vp, _i, _pvp],
     "ox_pipeline_destroy": [_vp],
     "ox_pipeline_run": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i],
+    "ox_pipeline_path": [_vp, C.POINTER(_i)],
+    "ox_pipeline_maps": [_vp, _pvp],
     "ox_pipeline_profile": [_vp, _vp, _i, _i, _i, C.POINTER(C.c_float)],
     "ox_pipeline_stats": [_vp, _pvp, _pvp, _pvp, C.POINTER(_i)],
     "ox_pipeline_stats_reset": [_vp],

@@ -169,7 +169,19 @@ struct ox_powerplan {
   ox::DevBuf partial, bp, window;
 };
 
+// state of the hand-written fused path (ox_fused.cu)
+struct FusedState {
+  bool ready = false, cov_symmetric = false;
+  int tw_len = 0;
+  ox::DevBuf tw;      // exp(-2 pi i j / tw_len)
+  ox::DevBuf covT;    // covsqrt transposed [nc][nc][nx][ny]
+  ox::DevBuf idxT;    // half-plane slot index transposed [nx/2+1][ny]
+  ox::DevBuf Ha, Hb;  // transposed half planes [max_batch][nc][nx/2+1][ny]
+};
+
 struct ox_pipeline {
+  int path = 0;       // 1 = cuFFT passes, 2 = fused hand-written FFT kernels
+  FusedState fused;
   ox_simplan *s = nullptr;
   ox_powerplan *p = nullptr;
   ox_binner *b = nullptr;
@@ -185,6 +197,14 @@ namespace ox {
 // sim: fill plan->kh for nsim sims from the chosen noise source (no FFT)
 int sim_fill_half(ox_simplan *p, const long long *seeds_host, int nsim, int noise_mode, const double *noise,
                   int noise_where, int flags);
+// sim: upload seeds / stage host noise for nsim sims
+int sim_stage_inputs(ox_simplan *p, const long long *seeds_host, int nsim, int noise_mode, const double *noise,
+                     int noise_where, const double **noise_dev);
+// fused path (ox_fused.cu)
+bool fused_supported(int ny, int nx, int ncomp, int dtype);
+int fused_prepare(ox_simplan *s, ox_binner *b, FusedState &fs);
+int fused_run(ox_pipeline *pl, int nsim, int noise_mode, const double *noise_dev, int flags, bool keep_maps,
+              cudaEvent_t *ev);
 // sim: kh -> real maps in p->maps
 int sim_to_maps(ox_simplan *p, int nsim);
 // power+bin from half-plane Fourier arrays on device -> bandpowers (device) [nbatch][nspec][nbins]

@@ -1,0 +1,725 @@
+// Fused hand-written path for sim -> FFT -> power2d -> bin2D on power-of-two maps.
+//
+// cuFFT's 2-D real transforms run at ~50% of their own two-pass HBM bound on B200
+// (40 us per 2048^2 fp64 transform), which alone would cap the pipeline at ~40% of its
+// roofline.  Here the four 1-D FFT passes are hand-written (ox_fft.cuh, shared-memory
+// Stockham radix-8) and fused with their producers and consumers, so a map costs three
+// kernels and ~4.s.N bytes of HBM traffic instead of ten passes:
+//
+//   K_A fused_sim_col : Philox/Box-Muller noise x covsqrt [x EB->QU] -> Hermitian k_h
+//                        generated straight into shared memory -> inverse FFT along y ->
+//                        written TRANSPOSED Ht[ix][y] (contiguous, coalesced)
+//   K_B fused_row     : tile of R rows: c2r inverse FFT along x (half-length complex FFT
+//                        + Hermitian packing) -> real map (optionally stored) x taper ->
+//                        r2c forward FFT along x -> written transposed Ht'[ix][y]
+//   K_C fused_col_bin : forward FFT along y of each column -> [QU->EB] -> conj(k_i) k_j ->
+//                        deterministic annular binning (warp-private slots, reduce_peers)
+//
+// The intermediate layout is the half plane transposed, [plane][ix = 0..Nx/2][iy = 0..Ny),
+// so K_A writes and K_C reads whole columns contiguously and only K_B touches R x 16 B
+// segments (R = 4 or 8 rows -> 64/128 B, sector aligned).
+#include <math.h>
+
+#include "ox_common.cuh"
+#include "ox_fft.cuh"
+
+using namespace ox;
+using namespace oxfft;
+
+namespace {
+
+// ---- shared helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+__device__ __forceinline__ void philox_normal2(unsigned long long seed, unsigned long long pix, unsigned comp,
+                                               unsigned stream, double &n1, double &n2) {
+  uint4 x = philox4x32_10(make_uint4((unsigned)pix, (unsigned)(pix >> 32), comp, stream),
+                          make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  unsigned long long a = ((unsigned long long)x.x << 32) | x.y;
+  unsigned long long b = ((unsigned long long)x.z << 32) | x.w;
+  double u1 = (double)((a >> 11) + 1ull) * 0x1.0p-53;
+  double u2 = (double)(b >> 11) * 0x1.0p-53;
+  double r = sqrt(-2.0 * log(u1));
+  double s, co;
+  sincospi(2.0 * u2, &s, &co);
+  n1 = r * co;
+  n2 = r * s;
+}
+
+__device__ __forceinline__ void rot_cs(double y, double x, double sgn, double &c, double &s) {
+  double l2 = y * y + x * x;
+  c = 1.0;
+  s = 0.0;
+  if (l2 > 0.0) {
+    double inv = 1.0 / l2;
+    c = (y * y - x * x) * inv;
+    s = sgn * (-2.0 * x * y) * inv;
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void reduce_peers(unsigned peers, double (&v)[NV]) {
+  const int lane = threadIdx.x & 31;
+  unsigned rel = __popc(peers & ((1u << lane) - 1u));
+  peers &= (lane == 31) ? 0u : (0xfffffffeu << lane);
+  while (__any_sync(0xffffffffu, peers)) {
+    int next = __ffs(peers);
+    int src = next ? next - 1 : lane;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      double t = __shfl_sync(0xffffffffu, v[k], src);
+      if (next) v[k] += t;
+    }
+    unsigned done = rel & 1u;
+    peers &= __ballot_sync(0xffffffffu, !done);
+    rel >>= 1;
+  }
+}
+
+// ---- K_A -------------------------------------------------------------------------------
+template <typename T>
+struct SimColArgs {
+  const T *covT;           // [NC][NC][nx][ny] covsqrt transposed (column ix contiguous in iy)
+  const double *noise;     // host-noise mode: [nsim][2][NC][ny][nx] natural layout
+  const long long *seeds;  // [nsim]
+  const double *ly, *lx;
+  const typename V2<T>::type *tw;  // exp(-2 pi i j / LT)
+  int tw_len;
+  int ny, nx, mx;  // mx = nx/2
+  int mode, rot, cov_symmetric;
+  double scale, rot_sgn;
+};
+
+template <typename T, int LY, int NC, int BPT>
+__global__ void __launch_bounds__(NC *(LY / 8 / BPT))
+fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[nsim][NC][mx+1][ny]*/) {
+  typedef typename V2<T>::type T2;
+  typedef BlockFFT<T, LY, BPT> FFT;
+  constexpr int NT = FFT::NT, NTHREADS = NC * NT, PS = padded_size(LY);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T2 *s = reinterpret_cast<T2 *>(smem_raw);  // [NC][PS]
+  const int ix = blockIdx.x, sim = blockIdx.y, tid = threadIdx.x;
+  const int mxp = ix ? a.nx - ix : 0;  // mirrored column
+  const long long n = (long long)a.ny * a.nx;
+  const unsigned long long seed = a.mode == OX_NOISE_HOST ? 0ull : (unsigned long long)a.seeds[sim];
+  const double h = 0.5 * a.scale;
+  for (int iy = tid; iy < LY; iy += NTHREADS) {
+    const int my = iy ? a.ny - iy : 0;
+    const long long p = (long long)iy * a.nx + ix, q = (long long)my * a.nx + mxp;
+    double pr[NC], pi[NC], qr[NC], qi[NC];
+    if (a.mode == OX_NOISE_HOST) {
+      const double *base = a.noise + (long long)sim * 2 * NC * n;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        pr[c] = base[(long long)c * n + p];
+        pi[c] = base[(long long)(NC + c) * n + p];
+        qr[c] = base[(long long)c * n + q];
+        qi[c] = base[(long long)(NC + c) * n + q];
+      }
+    } else if (a.mode == OX_NOISE_PHILOX) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        philox_normal2(seed, (unsigned long long)p, c, 0u, pr[c], pi[c]);
+        if (q == p) {
+          qr[c] = pr[c];
+          qi[c] = pi[c];
+        } else {
+          philox_normal2(seed, (unsigned long long)q, c, 0u, qr[c], qi[c]);
+        }
+      }
+    } else {
+      const bool conj_me = q < p;
+      const long long canon = conj_me ? q : p;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        double n1, n2;
+        philox_normal2(seed, (unsigned long long)canon, c, 1u, n1, n2);
+        if (q == p) {
+          pr[c] = n1;
+          pi[c] = 0.0;
+        } else {
+          pr[c] = n1 * 0.70710678118654752440;
+          pi[c] = (conj_me ? -n2 : n2) * 0.70710678118654752440;
+        }
+        qr[c] = pr[c];
+        qi[c] = -pi[c];
+      }
+    }
+    // k(p) = covsqrt(p) r(p), k(p') = covsqrt(p') r(p'); transposed covsqrt: [..][ix][iy]
+    double kpr[NC], kpi[NC], kqr[NC], kqi[NC];
+    const long long tp = (long long)ix * a.ny + iy, tq = (long long)mxp * a.ny + my;
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+      double sr = 0, si = 0, ur = 0, ui = 0;
+#pragma unroll
+      for (int j = 0; j < NC; j++) {
+        double cp = (double)a.covT[(long long)(i * NC + j) * n + tp];
+        double cq = a.cov_symmetric ? cp : (double)a.covT[(long long)(i * NC + j) * n + tq];
+        sr += cp * pr[j]; si += cp * pi[j];
+        ur += cq * qr[j]; ui += cq * qi[j];
+      }
+      kpr[i] = sr; kpi[i] = si; kqr[i] = ur; kqi[i] = ui;
+    }
+    if (NC == 3 && a.rot) {
+      double c, sn;
+      rot_cs(a.ly[iy], a.lx[ix], a.rot_sgn, c, sn);
+      double t1 = c * kpr[1] + sn * kpr[2], t2 = c * kpi[1] + sn * kpi[2];
+      double t3 = -sn * kpr[1] + c * kpr[2], t4 = -sn * kpi[1] + c * kpi[2];
+      kpr[1] = t1; kpi[1] = t2; kpr[2] = t3; kpi[2] = t4;
+      rot_cs(a.ly[my], a.lx[mxp], a.rot_sgn, c, sn);
+      t1 = c * kqr[1] + sn * kqr[2]; t2 = c * kqi[1] + sn * kqi[2];
+      t3 = -sn * kqr[1] + c * kqr[2]; t4 = -sn * kqi[1] + c * kqi[2];
+      kqr[1] = t1; kqi[1] = t2; kqr[2] = t3; kqi[2] = t4;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      T2 z;
+      z.x = (T)(h * (kpr[c] + kqr[c]));
+      z.y = (T)(h * (kpi[c] - kqi[c]));
+      s[c * PS + pad(iy)] = z;
+    }
+  }
+  __syncthreads();
+  const int f = tid / NT, t = tid - f * NT;
+  {
+    typename FFT::Twiddles tws;
+    tws.init(a.tw, a.tw_len / LY, t);
+    FFT::template run<+1>(s + f * PS, tws, t);
+  }
+  T2 *out = Ht + ((long long)sim * NC * (a.mx + 1) + ix) * a.ny;
+  for (int e = tid; e < NC * LY; e += NTHREADS) {
+    int c = e / LY, iy = e - c * LY;
+    out[(long long)c * (a.mx + 1) * a.ny + iy] = s[c * PS + pad(iy)];
+  }
+}
+
+// ---- K_B -------------------------------------------------------------------------------
+template <typename T>
+struct RowArgs {
+  const typename V2<T>::type *Hin;  // transposed half plane [plane][mx+1][ny] or null
+  const T *map_in;                  // real maps [plane][ny][nx] (used when Hin == null)
+  typename V2<T>::type *Hout;       // transposed half plane out or null
+  T *map_out;                       // real maps out (before the window) or null
+  const T *window;                  // [ny][nx] or null
+  const typename V2<T>::type *tw;
+  int tw_len;
+  int ny, nx, mx;
+};
+
+// R rows per CTA, each a length-MX complex FFT handled by NT threads
+template <typename T, int MX, int R, int BPT>
+__global__ void __launch_bounds__(R *(MX / 8 / BPT), (R * (MX / 8 / BPT) <= 512 ? 2 : 1))
+fused_row_kernel(RowArgs<T> a) {
+  typedef typename V2<T>::type T2;
+  typedef BlockFFT<T, MX, BPT> FFT;
+  constexpr int NT = FFT::NT, NTHREADS = R * NT, PS = padded_size(MX), NX = 2 * MX;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T2 *s = reinterpret_cast<T2 *>(smem_raw);  // [R][PS]
+  const int tid = threadIdx.x;
+  const int iy0 = blockIdx.x * R;
+  const long long plane = blockIdx.y;
+  const int f = tid / NT, t = tid - f * NT;
+  T2 *row = s + f * PS;
+  const int tws_n = a.tw_len / NX;  // stride for exp(-2 pi i k / Nx)
+  typename FFT::Twiddles tws;
+  tws.init(a.tw, a.tw_len / MX, t);
+  // the NT threads of one row synchronise among themselves only (named barriers need whole warps)
+  const int bar = (NT % 32 == 0) ? 1 + f : 0;
+  if (a.Hin) {
+    // tile load: for each ix the R rows are R*16 B contiguous in the transposed layout
+    const T2 *src = a.Hin + plane * (long long)(MX + 1) * a.ny + iy0;
+    for (int e = tid; e < (MX + 1) * R; e += NTHREADS) {
+      int ix = e / R, r = e - ix * R;
+      s[r * PS + pad(ix)] = src[(long long)ix * a.ny + r];
+    }
+    __syncthreads();
+    // Hermitian packing: Z[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/Nx} (X[k] - conj X[M-k])
+    for (int k = t; k <= MX / 2; k += NT) {
+      const int km = MX - k;
+      T2 xk = row[pad(k)], xm = row[pad(km)];
+      T2 w = a.tw[k * tws_n];
+      w.y = -w.y;  // e^{+2 pi i k/Nx}
+      T2 sum = cadd(xk, cconj(xm)), dif = csub(xk, cconj(xm));
+      T2 wd = mul_i<+1>(cmul(w, dif));
+      T2 zk = cadd(sum, wd);
+      // Z[M-k] = conj(sum) + i e^{+2 pi i (M-k)/Nx} (X[M-k] - conj X[k]) ; e^{2 pi i (M-k)/Nx} = -conj(w)
+      T2 zm = csub(cconj(sum), cconj(wd));
+      if (k == 0) {
+        row[pad(0)] = zk;  // X[M] consumed; slot M no longer needed
+      } else {
+        row[pad(k)] = zk;
+        if (km != k) row[pad(km)] = zm;
+      }
+    }
+    fft_sync(bar, NT);
+    FFT::template run<+1>(row, tws, t, bar);
+    // row[n] = x[2n] + i x[2n+1]
+  } else {
+    const T2 *src = reinterpret_cast<const T2 *>(a.map_in + (plane * a.ny + iy0) * (long long)NX);
+    for (int e = tid; e < MX * R; e += NTHREADS) {
+      int r = e / MX, n = e - r * MX;
+      s[r * PS + pad(n)] = src[(long long)r * MX + n];
+    }
+    __syncthreads();
+  }
+  if (a.map_out || a.window) {
+    // each row's threads handle their own row (no CTA-wide barrier needed)
+    const long long rowoff = (long long)(iy0 + f) * MX;
+    for (int n = t; n < MX; n += NT) {
+      T2 z = row[pad(n)];
+      if (a.map_out) reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX)[rowoff + n] = z;
+      if (a.window) {
+        T2 w = reinterpret_cast<const T2 *>(a.window)[rowoff + n];
+        z.x *= w.x;
+        z.y *= w.y;
+        row[pad(n)] = z;
+      }
+    }
+    fft_sync(bar, NT);
+  }
+  if (!a.Hout) return;
+  FFT::template run<-1>(row, tws, t, bar);
+  // unpack: X[k] = 1/2 [(Z[k] + conj Z[M-k]) - i e^{-2 pi i k/Nx} (Z[k] - conj Z[M-k])], k = 0..M
+  for (int k = t; k <= MX / 2; k += NT) {
+    const int km = MX - k;
+    T2 zk = row[pad(k)], zm = (k == 0) ? zk : row[pad(km)];
+    T2 w = a.tw[k * tws_n];  // e^{-2 pi i k/Nx}
+    T2 sum = cadd(zk, cconj(zm)), dif = csub(zk, cconj(zm));
+    T2 wd = mul_i<-1>(cmul(w, dif));
+    T2 xk = cadd(sum, wd);
+    // X[M-k] = 1/2 [conj(sum) - i e^{-2 pi i (M-k)/Nx} (Z[M-k] - conj Z[k])] ; the phase is -conj(w)
+    T2 xm = csub(cconj(sum), cconj(wd));
+    xk.x *= (T)0.5; xk.y *= (T)0.5; xm.x *= (T)0.5; xm.y *= (T)0.5;
+    row[pad(k)] = xk;
+    if (km != k) row[pad(km)] = xm;
+  }
+  __syncthreads();
+  T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + iy0;
+  for (int e = tid; e < (MX + 1) * R; e += NTHREADS) {
+    int ix = e / R, r = e - ix * R;
+    dst[(long long)ix * a.ny + r] = s[r * PS + pad(ix)];
+  }
+}
+
+// ---- K_C -------------------------------------------------------------------------------
+template <typename T>
+struct ColBinArgs {
+  const typename V2<T>::type *H;  // [nbatch][NC][mx+1][ny]
+  const uint16_t *idxT;           // [mx+1][ny]: slot | 0x8000 if Hermitian weight 2
+  const double *ly, *lx;
+  const typename V2<T>::type *tw;
+  int tw_len;
+  int ny, mx, nslots, cols_per_block, rot;
+  double rot_sgn;
+};
+
+template <typename T, int LY, int NC, int BPT>
+__global__ void __launch_bounds__(NC *(LY / 8 / BPT))
+fused_col_bin_kernel(ColBinArgs<T> a, double *__restrict__ partial /*[nbatch][gridDim.x][NS][nslots]*/) {
+  typedef typename V2<T>::type T2;
+  typedef BlockFFT<T, LY, BPT> FFT;
+  constexpr int NT = FFT::NT, NTHREADS = NC * NT, PS = padded_size(LY), NS = NC * (NC + 1) / 2, NWARPS = NTHREADS / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T2 *s = reinterpret_cast<T2 *>(smem_raw);                                           // [NC][PS]
+  double *bins = reinterpret_cast<double *>(smem_raw + sizeof(T2) * (size_t)NC * PS);  // [NWARPS][NS][nslots+1]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stride = a.nslots + 1;
+  double *mine = bins + (size_t)warp * NS * stride;
+  for (int i = lane; i < NS * stride; i += 32) mine[i] = 0.0;
+  const long long b = blockIdx.y;
+  const int f = tid / NT, t = tid - f * NT;
+  const int ix0 = blockIdx.x * a.cols_per_block;
+  const int ix1 = min(ix0 + a.cols_per_block, a.mx + 1);
+  typename FFT::Twiddles tws;
+  tws.init(a.tw, a.tw_len / LY, t);
+  // software pipeline: the next column is fetched into registers while this one is transformed and binned
+  constexpr int EPT = NC * LY / NTHREADS;  // elements per thread (8 * BPT)
+  T2 pre[EPT];
+  {
+    const T2 *src = a.H + (b * NC * (a.mx + 1) + ix0) * (long long)a.ny;
+#pragma unroll
+    for (int i = 0; i < EPT; i++) {
+      int e = tid + i * NTHREADS, c = e / LY, iy = e - c * LY;
+      pre[i] = src[(long long)c * (a.mx + 1) * a.ny + iy];
+    }
+  }
+  for (int ix = ix0; ix < ix1; ix++) {
+    __syncthreads();  // previous column's readers are done with s
+#pragma unroll
+    for (int i = 0; i < EPT; i++) {
+      int e = tid + i * NTHREADS, c = e / LY, iy = e - c * LY;
+      s[c * PS + pad(iy)] = pre[i];
+    }
+    if (ix + 1 < ix1) {
+      const T2 *src = a.H + (b * NC * (a.mx + 1) + ix + 1) * (long long)a.ny;
+#pragma unroll
+      for (int i = 0; i < EPT; i++) {
+        int e = tid + i * NTHREADS, c = e / LY, iy = e - c * LY;
+        pre[i] = src[(long long)c * (a.mx + 1) * a.ny + iy];
+      }
+    }
+    __syncthreads();
+    FFT::template run<-1>(s + f * PS, tws, t);
+    const uint16_t *idx = a.idxT + (long long)ix * a.ny;
+    const double x = a.lx[ix];
+    for (int base = 0; base < LY; base += NTHREADS) {
+      const int iy = base + tid;
+      unsigned key = a.nslots;
+      double v[NS];
+#pragma unroll
+      for (int q = 0; q < NS; q++) v[q] = 0.0;
+      if (iy < LY) {
+        unsigned raw = idx[iy];
+        key = raw & 0x7fffu;
+        const double w = (raw & 0x8000u) ? 2.0 : 1.0;
+        double re[NC], im[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          T2 z = s[c * PS + pad(iy)];
+          re[c] = (double)z.x;
+          im[c] = (double)z.y;
+        }
+        if (NC == 3 && a.rot) {
+          double c, sn;
+          rot_cs(a.ly[iy], x, a.rot_sgn, c, sn);
+          double er = c * re[1] - sn * re[2], ei = c * im[1] - sn * im[2];
+          double br = sn * re[1] + c * re[2], bi = sn * im[1] + c * im[2];
+          re[1] = er; im[1] = ei; re[2] = br; im[2] = bi;
+        }
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < NC; i++)
+#pragma unroll
+          for (int j = i; j < NC; j++) v[q++] = (re[i] * re[j] + im[i] * im[j]) * w;
+      }
+      unsigned peers = __match_any_sync(0xffffffffu, key);
+      bool leader = (__ffs(peers) - 1) == lane;
+      reduce_peers<NS>(peers, v);
+      if (leader) {
+#pragma unroll
+        for (int q = 0; q < NS; q++) mine[q * stride + key] += v[q];
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  double *out = partial + ((size_t)b * gridDim.x + blockIdx.x) * NS * a.nslots;
+  for (int i = tid; i < NS * a.nslots; i += NTHREADS) {
+    int sp = i / a.nslots, slot = i - sp * a.nslots;
+    double acc = 0.0;
+    for (int w = 0; w < NWARPS; w++) acc += bins[(size_t)w * NS * stride + sp * stride + slot];
+    out[i] = acc;
+  }
+}
+
+// ---- set-up kernels ----------------------------------------------------------------------
+template <typename T>
+__global__ void transpose_cov_kernel(const T *__restrict__ in, T *__restrict__ out, int ny, int nx, int nmat) {
+  // out[m][ix][iy] = in[m][iy][ix]
+  __shared__ T tile[32][33];
+  const int m = blockIdx.z;
+  int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+  const T *src = in + (long long)m * ny * nx;
+  T *dst = out + (long long)m * ny * nx;
+  for (int j = 0; j < 32; j += 8)
+    if (x < nx && y + j < ny) tile[threadIdx.y + j][threadIdx.x] = src[(long long)(y + j) * nx + x];
+  __syncthreads();
+  x = blockIdx.y * 32 + threadIdx.x;  // iy
+  y = blockIdx.x * 32 + threadIdx.y;  // ix
+  for (int j = 0; j < 32; j += 8)
+    if (x < ny && y + j < nx) dst[(long long)(y + j) * ny + x] = tile[threadIdx.x][threadIdx.y + j];
+}
+
+template <typename T>
+__global__ void cov_symmetry_kernel(const T *__restrict__ cov, int ny, int nx, int nmat, int *__restrict__ mismatch) {
+  long long n = (long long)ny * nx;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * nmat; i += (long long)gridDim.x * blockDim.x) {
+    long long m = i / n, p = i - m * n;
+    int iy = (int)(p / nx), ix = (int)(p - (long long)iy * nx);
+    int my = iy ? ny - iy : 0, mx = ix ? nx - ix : 0;
+    if (cov[i] != cov[m * n + (long long)my * nx + mx]) atomicAdd(mismatch, 1);
+  }
+}
+
+__global__ void transpose_idxh_kernel(const uint16_t *__restrict__ idxh, int ny, int nxh, uint16_t *__restrict__ out) {
+  long long n = (long long)ny * nxh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int ix = (int)(i / ny), iy = (int)(i - (long long)ix * ny);
+    out[i] = idxh[(long long)iy * nxh + ix];
+  }
+}
+
+template <typename T2>
+__global__ void bandpower_finalize2_kernel(const double *__restrict__ partial, int nblk, int ns, int nslots,
+                                           const double *__restrict__ count, double normfact, double *__restrict__ bp) {
+  // one warp per (map, spectrum, bin): lanes stride over the blocks, fixed shuffle tree
+  const int nbins = nslots - 2;
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  long long m = blockIdx.y;
+  if (gw >= ns * nbins) return;
+  int sp = gw / nbins, bin = gw - sp * nbins;
+  const double *p = partial + (size_t)m * nblk * ns * nslots + (size_t)sp * nslots + bin + 1;
+  double acc = 0.0;
+  for (int b = lane; b < nblk; b += 32) acc += p[(size_t)b * ns * nslots];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) bp[(size_t)m * ns * nbins + gw] = (acc * normfact) / count[bin + 1];
+}
+
+template <typename F>
+int set_smem(F kernel, size_t bytes) {
+  if (bytes > 48 * 1024) OX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return OX_OK;
+}
+
+constexpr size_t SMEM_MAX = 227 * 1024;
+
+// BPT choice: keep threads per CTA <= 512 where possible
+template <typename T, int LY, int NC>
+struct ColCfg {
+  static constexpr int BPT = (NC * (LY / 8) > 512) ? ((NC * (LY / 8) > 1024) ? 4 : 2) : 1;
+};
+
+template <typename T, int LY, int NC>
+int launch_sim_col(SimColArgs<T> &a, void *Ht, int nsim) {
+  constexpr int BPT = ColCfg<T, LY, NC>::BPT;
+  typedef typename V2<T>::type T2;
+  size_t smem = sizeof(T2) * NC * padded_size(LY);
+  OX_REQUIRE(smem <= SMEM_MAX, "fused sim: column of %d x %d comps needs %zu B of shared memory", LY, NC, smem);
+  auto k = fused_sim_col_kernel<T, LY, NC, BPT>;
+  OX_TRY(set_smem(k, smem));
+  dim3 grid(a.mx + 1, nsim);
+  k<<<grid, NC * (LY / 8 / BPT), smem, g_stream>>>(a, (T2 *)Ht);
+  OX_KERNEL_CHECK();
+  return OX_OK;
+}
+
+template <typename T, int LY, int NC>
+int launch_col_bin(ColBinArgs<T> &a, double *partial, int nbatch, int nblk) {
+  constexpr int BPT = ColCfg<T, LY, NC>::BPT;
+  typedef typename V2<T>::type T2;
+  constexpr int NTHREADS = NC * (LY / 8 / BPT), NS = NC * (NC + 1) / 2;
+  size_t smem = sizeof(T2) * NC * padded_size(LY) + sizeof(double) * (NTHREADS / 32) * NS * (a.nslots + 1);
+  OX_REQUIRE(smem <= SMEM_MAX, "fused bin: %d slots x %d spectra need %zu B of shared memory", a.nslots, NS, smem);
+  auto k = fused_col_bin_kernel<T, LY, NC, BPT>;
+  OX_TRY(set_smem(k, smem));
+  dim3 grid(nblk, nbatch);
+  k<<<grid, NTHREADS, smem, g_stream>>>(a, partial);
+  OX_KERNEL_CHECK();
+  return OX_OK;
+}
+
+template <typename T, int MX>
+int launch_row(RowArgs<T> &a, long long nplanes) {
+  typedef typename V2<T>::type T2;
+  // rows per CTA: 64-byte segments (4 x double2 / 8 x float2)
+  constexpr int R = sizeof(T2) == 16 ? 4 : 8;
+  constexpr int BPT = (R * (MX / 8) > 512) ? ((R * (MX / 8) > 1024) ? 4 : 2) : 1;
+  size_t smem = sizeof(T2) * R * padded_size(MX);
+  OX_REQUIRE(smem <= SMEM_MAX, "fused row: %d rows of %d need %zu B of shared memory", R, MX, smem);
+  OX_REQUIRE(a.ny % R == 0, "ny must be a multiple of %d", R);
+  auto k = fused_row_kernel<T, MX, R, BPT>;
+  OX_TRY(set_smem(k, smem));
+  dim3 grid(a.ny / R, (unsigned)nplanes);
+  k<<<grid, R * (MX / 8 / BPT), smem, g_stream>>>(a);
+  OX_KERNEL_CHECK();
+  return OX_OK;
+}
+
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+// =========================================================================================
+namespace ox {
+
+bool fused_supported(int ny, int nx, int ncomp, int dtype) {
+  if (!pow2(ny) || !pow2(nx)) return false;
+  if (ny < 256 || ny > 4096 || nx < 256 || nx > 8192) return false;
+  if (ncomp != 1 && ncomp != 3) return false;
+  size_t es = dtype == OX_F32 ? 8 : 16;
+  if (es * ncomp * padded_size(ny) + 64 * 1024 > SMEM_MAX && ncomp == 3) return false;
+  if (es * padded_size(ny) > SMEM_MAX) return false;
+  return true;
+}
+
+int fused_make_twiddles(int len, int dtype, DevBuf &buf) {
+  size_t es = dtype == OX_F32 ? 8 : 16;
+  OX_TRY(buf.ensure(es * len));
+  std::vector<double> h(2 * (size_t)len);
+  const long double tau = 6.283185307179586476925286766559005768394L;
+  for (int j = 0; j < len; j++) {
+    // exact octant symmetries keep the table accurate to < 1 ulp
+    long double ang = -tau * (long double)j / (long double)len;
+    h[2 * j] = (double)cosl(ang);
+    h[2 * j + 1] = (double)sinl(ang);
+  }
+  if (dtype == OX_F64) {
+    OX_CUDA(cudaMemcpyAsync(buf.p, h.data(), es * len, cudaMemcpyHostToDevice, g_stream));
+  } else {
+    std::vector<float> hf(2 * (size_t)len);
+    for (size_t i = 0; i < hf.size(); i++) hf[i] = (float)h[i];
+    OX_CUDA(cudaMemcpyAsync(buf.p, hf.data(), es * len, cudaMemcpyHostToDevice, g_stream));
+    OX_CUDA(cudaStreamSynchronize(g_stream));
+  }
+  OX_CUDA(cudaStreamSynchronize(g_stream));
+  return OX_OK;
+}
+
+template <typename T>
+static int prepare_cov_T(ox_simplan *p, FusedState &fs) {
+  ox_geometry *g = p->g;
+  int nmat = p->ncomp * p->ncomp;
+  size_t nel = (size_t)nmat * g->ny * g->nx;
+  OX_TRY(fs.covT.ensure(sizeof(T) * nel));
+  dim3 grid((g->nx + 31) / 32, (g->ny + 31) / 32, nmat), block(32, 8);
+  transpose_cov_kernel<T><<<grid, block, 0, g_stream>>>(p->covsqrt.as<T>(), fs.covT.as<T>(), g->ny, g->nx, nmat);
+  OX_KERNEL_CHECK();
+  DevBuf mism;
+  OX_TRY(mism.ensure(sizeof(int)));
+  OX_CUDA(cudaMemsetAsync(mism.p, 0, sizeof(int), g_stream));
+  cov_symmetry_kernel<T><<<sm_count() * 8, 256, 0, g_stream>>>(p->covsqrt.as<T>(), g->ny, g->nx, nmat, mism.as<int>());
+  OX_KERNEL_CHECK();
+  int h = 0;
+  OX_CUDA(cudaMemcpyAsync(&h, mism.p, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  OX_CUDA(cudaStreamSynchronize(g_stream));
+  fs.cov_symmetric = (h == 0);
+  return OX_OK;
+}
+
+int fused_prepare(ox_simplan *s, ox_binner *b, FusedState &fs) {
+  ox_geometry *g = s->g;
+  fs.tw_len = g->ny > g->nx ? g->ny : g->nx;
+  OX_TRY(fused_make_twiddles(fs.tw_len, s->dtype, fs.tw));
+  if (s->dtype == OX_F64) OX_TRY(prepare_cov_T<double>(s, fs));
+  else OX_TRY(prepare_cov_T<float>(s, fs));
+  long long nh = (long long)g->ny * g->nxh;
+  OX_TRY(fs.idxT.ensure(sizeof(uint16_t) * nh));
+  transpose_idxh_kernel<<<sm_count() * 8, 256, 0, g_stream>>>(b->idxh.as<uint16_t>(), g->ny, g->nxh, fs.idxT.as<uint16_t>());
+  OX_KERNEL_CHECK();
+  size_t es = elem_size(s->dtype);
+  size_t hbytes = 2 * es * (size_t)s->max_batch * s->ncomp * g->nxh * g->ny;
+  OX_TRY(fs.Ha.ensure(hbytes));
+  OX_TRY(fs.Hb.ensure(hbytes));
+  fs.ready = true;
+  return OX_OK;
+}
+
+template <typename T>
+static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *noise_dev, int flags, bool keep_maps,
+                       cudaEvent_t *ev) {
+  typedef typename V2<T>::type T2;
+  ox_simplan *s = pl->s;
+  ox_geometry *g = s->g;
+  FusedState &fs = pl->fused;
+  const int nc = s->ncomp;
+#define OX_MARK(i) do { if (ev) OX_CUDA(cudaEventRecord(ev[i], g_stream)); } while (0)
+  OX_MARK(0);
+  SimColArgs<T> sa;
+  sa.covT = fs.covT.as<T>();
+  sa.noise = noise_dev;
+  sa.seeds = s->seeds.as<long long>();
+  sa.ly = g->ly.as<double>();
+  sa.lx = g->lx.as<double>();
+  sa.tw = fs.tw.as<T2>();
+  sa.tw_len = fs.tw_len;
+  sa.ny = g->ny; sa.nx = g->nx; sa.mx = g->nx / 2;
+  sa.mode = noise_mode;
+  sa.rot = (flags & OX_FLAG_ROT) ? 1 : 0;
+  sa.cov_symmetric = fs.cov_symmetric ? 1 : 0;
+  sa.scale = 1.0 / sqrt((double)g->ny * (double)g->nx);
+  sa.rot_sgn = (flags & OX_FLAG_IAU) ? 1.0 : -1.0;
+  int st = OX_ERR_UNSUPPORTED;
+#define OX_SIMCOL(LY)                                                                     \
+  case LY:                                                                                \
+    st = nc == 1 ? launch_sim_col<T, LY, 1>(sa, fs.Ha.p, nsim) : launch_sim_col<T, LY, 3>(sa, fs.Ha.p, nsim); \
+    break;
+  switch (g->ny) {
+    OX_SIMCOL(256) OX_SIMCOL(512) OX_SIMCOL(1024) OX_SIMCOL(2048) OX_SIMCOL(4096)
+    default: set_error("fused path: unsupported ny=%d", g->ny);
+  }
+#undef OX_SIMCOL
+  OX_TRY(st);
+  OX_MARK(1);
+  RowArgs<T> ra;
+  ra.Hin = fs.Ha.as<T2>();
+  ra.map_in = nullptr;
+  ra.Hout = fs.Hb.as<T2>();
+  ra.map_out = nullptr;
+  if (keep_maps) {
+    OX_TRY(s->maps.ensure(elem_size(s->dtype) * (size_t)s->max_batch * nc * g->ny * g->nx));
+    ra.map_out = s->maps.as<T>();
+  }
+  ra.window = pl->has_window ? pl->window.as<T>() : nullptr;
+  ra.tw = fs.tw.as<T2>();
+  ra.tw_len = fs.tw_len;
+  ra.ny = g->ny; ra.nx = g->nx; ra.mx = g->nx / 2;
+  st = OX_ERR_UNSUPPORTED;
+  switch (g->nx / 2) {
+    case 128: st = launch_row<T, 128>(ra, (long long)nsim * nc); break;
+    case 256: st = launch_row<T, 256>(ra, (long long)nsim * nc); break;
+    case 512: st = launch_row<T, 512>(ra, (long long)nsim * nc); break;
+    case 1024: st = launch_row<T, 1024>(ra, (long long)nsim * nc); break;
+    case 2048: st = launch_row<T, 2048>(ra, (long long)nsim * nc); break;
+    case 4096: st = launch_row<T, 4096>(ra, (long long)nsim * nc); break;
+    default: set_error("fused path: unsupported nx=%d", g->nx);
+  }
+  OX_TRY(st);
+  OX_MARK(2);
+  OX_MARK(3);
+  OX_MARK(4);
+  ColBinArgs<T> ca;
+  ca.H = fs.Hb.as<T2>();
+  ca.idxT = fs.idxT.as<uint16_t>();
+  ca.ly = g->ly.as<double>();
+  ca.lx = g->lx.as<double>();
+  ca.tw = fs.tw.as<T2>();
+  ca.tw_len = fs.tw_len;
+  ca.ny = g->ny; ca.mx = g->nx / 2;
+  ca.nslots = pl->b->nslots;
+  ca.cols_per_block = 8;
+  ca.rot = (flags & OX_FLAG_ROT) ? 1 : 0;
+  ca.rot_sgn = sa.rot_sgn;
+  int nblk = (g->nxh + ca.cols_per_block - 1) / ca.cols_per_block;
+  int ns = nc * (nc + 1) / 2;
+  OX_TRY(pl->partial.ensure(sizeof(double) * (size_t)nsim * nblk * ns * pl->b->nslots));
+  st = OX_ERR_UNSUPPORTED;
+#define OX_COLBIN(LY)                                                                                              \
+  case LY:                                                                                                         \
+    st = nc == 1 ? launch_col_bin<T, LY, 1>(ca, pl->partial.as<double>(), nsim, nblk)                              \
+                 : launch_col_bin<T, LY, 3>(ca, pl->partial.as<double>(), nsim, nblk);                             \
+    break;
+  switch (g->ny) {
+    OX_COLBIN(256) OX_COLBIN(512) OX_COLBIN(1024) OX_COLBIN(2048) OX_COLBIN(4096)
+    default: set_error("fused path: unsupported ny=%d", g->ny);
+  }
+#undef OX_COLBIN
+  OX_TRY(st);
+  int nbins = pl->b->nslots - 2;
+  dim3 grid((ns * nbins * 32 + 255) / 256, nsim);
+  bandpower_finalize2_kernel<T2><<<grid, 256, 0, g_stream>>>(pl->partial.as<double>(), nblk, ns, pl->b->nslots,
+                                                             pl->b->invcount.as<double>(), pl->p->normfact, pl->bp.as<double>());
+  OX_KERNEL_CHECK();
+  OX_MARK(5);
+#undef OX_MARK
+  return OX_OK;
+}
+
+int fused_run(ox_pipeline *pl, int nsim, int noise_mode, const double *noise_dev, int flags, bool keep_maps,
+              cudaEvent_t *ev) {
+  if (pl->s->dtype == OX_F64) return fused_run_T<double>(pl, nsim, noise_mode, noise_dev, flags, keep_maps, ev);
+  return fused_run_T<float>(pl, nsim, noise_mode, noise_dev, flags, keep_maps, ev);
+}
+
+}  // namespace ox

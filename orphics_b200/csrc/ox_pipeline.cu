@@ -5,6 +5,8 @@
 // HBM passes per T-only map (s = bytes per real, N = Ny*Nx):
 //   sim_fill writes k_h (sN) -> cuFFT Z2D (2 passes) -> window RMW (2sN, optional) ->
 //   cuFFT D2Z (2 passes) -> power_bin reads k_h (sN) + uint16 slot index (N).
+#include <stdlib.h>
+
 #include "ox_common.cuh"
 
 using namespace ox;
@@ -67,6 +69,18 @@ int ox_pipeline_create(ox_simplan *s, ox_powerplan *p, ox_binner *b, const doubl
   if ((st = pl->stat_sum.ensure(sizeof(double) * d)) != OX_OK) return fail(st);
   if ((st = pl->stat_cross.ensure(sizeof(double) * d * d)) != OX_OK) return fail(st);
   if ((st = pl->bp.ensure(sizeof(double) * d * s->max_batch)) != OX_OK) return fail(st);
+  // hand-written fused FFT path when the geometry allows it (ORPHX_PIPELINE=cufft|fused overrides)
+  pl->path = 1;
+  const char *env = getenv("ORPHX_PIPELINE");
+  bool want_fused = fused_supported(s->g->ny, s->g->nx, s->ncomp, s->dtype) && !(env && !strcmp(env, "cufft"));
+  if (env && !strcmp(env, "fused") && !want_fused) {
+    set_error("ORPHX_PIPELINE=fused but %dx%d x%d comps is not supported by the fused path", s->g->ny, s->g->nx, s->ncomp);
+    return fail(OX_ERR_UNSUPPORTED);
+  }
+  if (want_fused) {
+    if ((st = fused_prepare(s, b, pl->fused)) != OX_OK) return fail(st);
+    pl->path = 2;
+  }
   *out = pl;
   return ox_pipeline_stats_reset(pl);
 }
@@ -102,6 +116,19 @@ static int pipeline_run_impl(ox_pipeline *pl, const long long *seeds, int nsim, 
   ox_geometry *g = s->g;
   OX_REQUIRE(nsim >= 1 && nsim <= s->max_batch && nsim <= p->max_batch, "nsim=%d outside 1..max_batch", nsim);
   size_t es = elem_size(s->dtype);
+  if (pl->path == 2) {
+    const double *noise_dev;
+    OX_TRY(sim_stage_inputs(s, seeds, nsim, noise_mode, noise, noise_where, &noise_dev));
+    OX_REQUIRE(!(flags & OX_FLAG_ROT) || s->ncomp == 3, "EB->QU rotation needs ncomp == 3");
+    OX_TRY(fused_run(pl, nsim, noise_mode, noise_dev, flags, (flags & OX_FLAG_KEEP_MAPS) != 0, ev));
+    long long total2 = (long long)pl->dim * pl->dim;
+    stats_accumulate_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, g_stream>>>(
+        pl->bp.as<double>(), nsim, pl->dim, pl->stat_n.as<long long>(), pl->stat_sum.as<double>(), pl->stat_cross.as<double>());
+    OX_KERNEL_CHECK();
+    if (ev) OX_CUDA(cudaEventRecord(ev[6], g_stream));
+    if (bandpowers) OX_TRY(stage_out(bandpowers, out_where, pl->bp.p, sizeof(double) * (size_t)nsim * pl->dim));
+    return OX_OK;
+  }
 #define OX_MARK(i) do { if (ev) OX_CUDA(cudaEventRecord(ev[i], g_stream)); } while (0)
   OX_MARK(0);
   // 1. k_h = Hermitian part of covsqrt.noise / sqrt(Npix)          (hand-written)
@@ -136,6 +163,18 @@ static int pipeline_run_impl(ox_pipeline *pl, const long long *seeds, int nsim, 
 int ox_pipeline_run(ox_pipeline *pl, const long long *seeds, int nsim, int noise_mode, const double *noise, int noise_where,
                     int flags, double *bandpowers, int out_where) {
   return pipeline_run_impl(pl, seeds, nsim, noise_mode, noise, noise_where, flags, bandpowers, out_where, nullptr);
+}
+
+int ox_pipeline_path(ox_pipeline *pl, int *path) {
+  OX_REQUIRE(pl && path, "null pointer");
+  *path = pl->path;
+  return OX_OK;
+}
+
+int ox_pipeline_maps(ox_pipeline *pl, void **maps_dev) {
+  OX_REQUIRE(pl && maps_dev, "null pointer");
+  *maps_dev = pl->s->maps.p;
+  return OX_OK;
 }
 
 int ox_pipeline_profile(ox_pipeline *pl, const long long *seeds, int nsim, int noise_mode, int flags, float *stage_ms) {

@@ -296,6 +296,11 @@ int prepare_inputs(ox_simplan *p, const long long *seeds_host, int nsim, int mod
 
 namespace ox {
 
+int sim_stage_inputs(ox_simplan *p, const long long *seeds_host, int nsim, int noise_mode, const double *noise,
+                     int noise_where, const double **noise_dev) {
+  return prepare_inputs(p, seeds_host, nsim, noise_mode, noise, noise_where, noise_dev);
+}
+
 int sim_fill_half(ox_simplan *p, const long long *seeds_host, int nsim, int noise_mode, const double *noise,
                   int noise_where, int flags) {
   const double *noise_dev;

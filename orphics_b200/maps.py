@@ -484,23 +484,37 @@ class SimPipeline(object):
         self.nspec = mapgen.ncomp * (mapgen.ncomp + 1) // 2
         self.nbins = binner.centers.size
         self.dim = self.nspec * self.nbins
+        path = C.c_int(0)
+        check(lib.ox_pipeline_path(self.handle, C.byref(path)))
+        #: "fused" = hand-written FFT kernels (power-of-two maps), "cufft" = cuFFT passes
+        self.path = {1: "cufft", 2: "fused"}[path.value]
 
-    def _flags(self, scalar, iau):
-        f = 0
+    def last_maps(self, nsim):
+        """Real-space maps (before the taper) of the last run of nsim sims (needs
+        keep_maps=True on the fused path)."""
+        p = C.c_void_p()
+        check(lib.ox_pipeline_maps(self.handle, C.byref(p)))
+        mg = self.mapgen
+        out = np.empty((nsim, mg.ncomp) + mg.geometry.shape, dtype=_capi.np_dtype(mg.dtype))
+        check(lib.ox_memcpy_d2h(ptr(out), p, out.nbytes))
+        return out
+
+    def _flags(self, scalar, iau, keep_maps=False):
+        f = _capi.FLAG_KEEP_MAPS if keep_maps else 0
         if not scalar and self.mapgen.ncomp == 3:
             f |= _capi.FLAG_ROT
         if iau:
             f |= _capi.FLAG_IAU
         return f
 
-    def run(self, seeds, scalar=False, iau=False, noise=None, out=None, fetch=True):
+    def run(self, seeds, scalar=False, iau=False, noise=None, out=None, fetch=True, keep_maps=False):
         """Bandpowers of len(seeds) sims.  noise: None -> the MapGen's mode."""
         mg = self.mapgen
         mode = _capi.NOISE_MODES[noise or mg.noise]
         seeds = list(seeds)
         nsim = len(seeds)
         res = np.empty((nsim, self.nspec, self.nbins), dtype=np.float64) if out is None else out
-        flags = self._flags(scalar, iau)
+        flags = self._flags(scalar, iau, keep_maps)
         done = 0
         while done < nsim:
             n = min(mg.max_batch, nsim - done)

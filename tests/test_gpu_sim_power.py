@@ -176,12 +176,16 @@ def test_philox_modes_match_oracle_noise(mode, pol, theory):
     assert relerr(kh[0], og.map_from_noise(oenmap.ndmap(rand if pol else rand[0], wo), harm=True)) < TOL64
 
 
+@pytest.mark.parametrize("path", ["cufft", "fused"])
 @pytest.mark.parametrize("pol", [False, True])
-def test_fused_pipeline_matches_oracle_and_accumulates_statistics(pol, theory):
+def test_fused_pipeline_matches_oracle_and_accumulates_statistics(pol, path, theory, monkeypatch):
     """BASELINE config 2 path at test size: seeds -> bandpowers in one call, with taper,
-    in seed-parity (numpy noise) and Philox modes; Statistics triple on the device."""
+    in seed-parity (numpy noise) and Philox modes; Statistics triple on the device.
+    Both implementations: cuFFT passes, and the hand-written fused FFT kernels."""
     from orphics_b200 import maps, stats
-    shape, wcs, so, wo, modl, ps = setup(128, 2.0, pol, theory)
+    monkeypatch.setenv("ORPHX_PIPELINE", path)
+    npix = 256
+    shape, wcs, so, wo, modl, ps = setup(npix, 2.0, pol, theory)
     taper, w2 = maps.get_taper(shape, wcs)
     otaper = np.asarray(omaps.get_taper(so, wo)[0])
     edges = np.arange(200, 2600, 100.0)
@@ -199,17 +203,21 @@ def test_fused_pipeline_matches_oracle_and_accumulates_statistics(pol, theory):
         fc = maps.FourierCalc(shape, wcs, max_batch=4)
         b = stats.bin2D(fc.geometry.modlmap(), edges, geometry=fc.geometry)
         pipe = maps.SimPipeline(mg, fc, b, window=np.asarray(taper))
+        assert pipe.path == path
         seeds = [1000 + i for i in range(6)]            # 6 sims with max_batch 4: two chunks
-        bp = pipe.run(seeds)
+        bp = pipe.run(seeds, keep_maps=True)
         assert bp.shape == (6, len(pairs), len(edges) - 1)
         want = []
         for s in seeds:
             if mode == "numpy":
                 mo = og.get_map(seed=s)
             else:
-                rand = philox_np.noise_field(s, 3 if pol else 1, 128, 128, hermitian=(mode == "philox_hermitian"))
+                rand = philox_np.noise_field(s, 3 if pol else 1, npix, npix, hermitian=(mode == "philox_hermitian"))
                 mo = og.map_from_noise(oenmap.ndmap(rand if pol else rand[0], wo))
             want.append(oracle_bp(mo))
+        if path == "fused":
+            last = pipe.last_maps(2)                     # sims 5,6 (second chunk), before the taper
+            assert relerr(last[1] if pol else last[1, 0], mo) < TOL64
         want = np.array(want)
         auto = {0: 0, 1: 3, 2: 5}
         for s, (i, j) in enumerate(pairs):
@@ -257,9 +265,11 @@ def test_sim_power_bin_recovers_theory_philox(theory):
         bp = pipe.run(range(64))[:, 0]
         ratio = bp.mean(0) / theory.lCl("TT", b.centers)
         assert abs(ratio.mean() - 1) < 0.01, ratio.mean()
+        # exact expectation of the estimator: E[p2d] = covsqrt^2 * area / Npix, binned
+        expect = b.bin(np.asarray(mg.covsqrt)[0, 0] ** 2 * fc.geometry.area / fc.geometry.npix)[1]
         nmodes = b.slot_counts[1:-1]
         sigma = np.sqrt(2.0 / (nmodes * 64.0))           # Gaussian-field bandpower scatter
-        assert np.all(np.abs(ratio - 1) < 5 * sigma + 0.01)
+        assert np.all(np.abs(bp.mean(0) / expect - 1) < 5 * sigma)
 
 
 def test_large_map_properties_2048(theory):
