@@ -204,9 +204,15 @@ power_bin_half_kernel(const T2 *__restrict__ k1, const T2 *__restrict__ k2, cons
     double v[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) v[s] = 0.0;
+    unsigned raw = 0;
     if (i < end) {
-      unsigned raw = idxh[i];
+      raw = idxh[i];
       key = raw & 0x7fffu;
+      // slots 0 and nslots-1 are dropped by bin2D's [1:-1] (stats.py:796-797)
+      if (key == 0u || key == (unsigned)(nslots - 1)) key = nslots;
+    }
+    if (__all_sync(0xffffffffu, key == (unsigned)nslots)) continue;
+    if (key != (unsigned)nslots) {
       double w = (raw & 0x8000u) ? 2.0 : 1.0;
       double ar[NC], ai[NC], br[NC], bi[NC];
 #pragma unroll

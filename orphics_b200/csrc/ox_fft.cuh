@@ -1,20 +1,23 @@
 // Block-level FFT engine for the fused sim -> FFT -> power -> bin kernels (ox_fused.cu).
 //
-// A power-of-two complex FFT of length L lives in shared memory; L/8 "units" of 8
-// elements are processed per stage by a Stockham autosort radix-8 (then 4 or 2) pass:
-//   read 8 strided elements -> twiddle -> butterfly in registers -> barrier ->
-//   write to the autosorted positions -> barrier.
-// Reads of a stage are contiguous across lanes; the stride-R writes of the first stage
-// would be 8..32-way bank conflicts, so the buffer is padded by one element every 8
-// (pad(e) = e + e/8), which makes every access pattern of every stage conflict-free for
-// both 16-byte (double2) and 8-byte (float2) elements.
-//
-// Twiddles: a thread works on the same butterflies in every transform it takes part in,
-// so its first-order twiddle w = exp(-2 pi i k / (Ns R)) of every stage is loaded ONCE from
-// a global table (tw[j] = exp(-2 pi i j / LT), built on the host in long double) into
-// registers (Twiddles::init); w^2..w^7 are formed by complex multiplications in the stage.
-// (Loading all seven per butterfly from the table made the kernels L1-bound: ncu showed
-// 4.7x more L1 sectors for twiddles than for data.)  DIR = -1 forward, +1 backward.
+// A power-of-two complex FFT of length L = 16^a * rem (rem in {1,2,4,8}) is executed by
+// L/16 threads, each holding a "unit" of 16 elements in registers.  Stages are Stockham
+// autosort passes: radix 16 while possible, then one radix-rem stage; between stages the
+// data is exchanged through shared memory (write to the autosorted positions, barrier,
+// contiguous read).  Shared-memory bandwidth is what bounds these kernels on B200 (ncu:
+// L1/shared pipe 75% busy with the earlier radix-8 engine, FP64 pipe 20%), so the design
+// minimises round trips:
+//   * radix 16 -> 2 exchanges for L <= 2048 (the radix-8 version needed 3-4);
+//   * the first stage takes its input from a caller-supplied functor (registers: generated
+//     noise, global memory, or a packed view of shared memory) and the last stage hands its
+//     output to a functor (global store, window multiply, binning) -- no extra passes;
+//   * buffers are padded by one element every 16 (pad(e) = e + e/16): the stride-16 writes
+//     of the first stage and every contiguous read are bank-conflict free for 16 B and 8 B
+//     elements.
+// Twiddles: a thread works on the same butterflies in every transform, so the first-order
+// twiddle w = exp(-2 pi i k / (Ns R)) of each stage is loaded once from a global table
+// (tw[j] = exp(-2 pi i j / LT), built on the host in long double) into registers; w^2..w^15
+// are formed by complex multiplications.  DIR = -1 forward, +1 backward (unnormalised).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -31,11 +34,12 @@ struct V2<float> {
   typedef float2 type;
 };
 
-__host__ __device__ constexpr int pad(int e) { return e + (e >> 3); }
+__host__ __device__ constexpr int pad(int e) { return e + (e >> 4); }
 // elements to allocate for one padded length-L buffer that may also hold index L (the
-// Nyquist element of a real transform); the +2 makes consecutive buffers start 32 bytes
-// apart modulo 128 for double2 so that equal indices of neighbouring rows hit different banks
-__host__ __device__ constexpr int padded_size(int L) { return L + (L >> 3) + 2; }
+// Nyquist element of a real transform); sizes are kept = 2 (mod 8) so that consecutive
+// double2 buffers start 32 bytes apart modulo 128 and equal indices of neighbouring rows
+// fall into different banks
+__host__ __device__ constexpr int padded_size(int L) { return ((L + (L >> 4) + 1 + 7) / 8) * 8 + 2; }
 
 template <typename T2>
 __device__ __forceinline__ T2 cadd(T2 a, T2 b) {
@@ -76,44 +80,50 @@ __device__ __forceinline__ T2 mul_i(T2 a) {
   }
   return r;
 }
-
-template <int DIR, typename T2>
-__device__ __forceinline__ void bfly2(T2 (&v)[8], int o) {
-  T2 a = v[o], b = v[o + 1];
-  v[o] = cadd(a, b);
-  v[o + 1] = csub(a, b);
+// multiply by (c + DIR*i*s)
+template <int DIR, typename T2, typename T>
+__device__ __forceinline__ T2 mul_cs(T2 a, T c, T s) {
+  T2 r;
+  if (DIR > 0) {
+    r.x = a.x * c - a.y * s;
+    r.y = a.y * c + a.x * s;
+  } else {
+    r.x = a.x * c + a.y * s;
+    r.y = a.y * c - a.x * s;
+  }
+  return r;
 }
 
-// radix-4 DFT of v[o..o+3] (natural order in and out)
 template <int DIR, typename T2>
-__device__ __forceinline__ void bfly4(T2 (&v)[8], int o) {
-  T2 a0 = cadd(v[o], v[o + 2]), a2 = csub(v[o], v[o + 2]);
-  T2 a1 = cadd(v[o + 1], v[o + 3]), a3 = mul_i<DIR>(csub(v[o + 1], v[o + 3]));
-  v[o] = cadd(a0, a1);
-  v[o + 1] = cadd(a2, a3);
-  v[o + 2] = csub(a0, a1);
-  v[o + 3] = csub(a2, a3);
+__device__ __forceinline__ void dft2(T2 &a, T2 &b) {
+  T2 t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
 }
 
-// radix-8 DFT of v[0..7] (natural order in and out)
+// 4-point DFT, natural order in and out
 template <int DIR, typename T2>
-__device__ __forceinline__ void bfly8(T2 (&v)[8]) {
+__device__ __forceinline__ void dft4(T2 &x0, T2 &x1, T2 &x2, T2 &x3) {
+  T2 a0 = cadd(x0, x2), a2 = csub(x0, x2);
+  T2 a1 = cadd(x1, x3), a3 = mul_i<DIR>(csub(x1, x3));
+  x0 = cadd(a0, a1);
+  x1 = cadd(a2, a3);
+  x2 = csub(a0, a1);
+  x3 = csub(a2, a3);
+}
+
+// 8-point DFT, natural order in and out
+template <int DIR, typename T2>
+__device__ __forceinline__ void dft8(T2 *v) {
   typedef decltype(v[0].x) T;
   const T h = (T)0.70710678118654752440;
   T2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
   T2 a1 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
   T2 a2 = cadd(v[2], v[6]), a6 = csub(v[2], v[6]);
   T2 a3 = cadd(v[3], v[7]), a7 = csub(v[3], v[7]);
-  // a5 *= e^{DIR i pi/4}, a6 *= e^{DIR i pi/2}, a7 *= e^{DIR 3 i pi/4}
-  T2 t;
-  if (DIR > 0) {
-    t.x = h * (a5.x - a5.y); t.y = h * (a5.x + a5.y); a5 = t;
-    t.x = -h * (a7.x + a7.y); t.y = h * (a7.x - a7.y); a7 = t;
-  } else {
-    t.x = h * (a5.x + a5.y); t.y = h * (a5.y - a5.x); a5 = t;
-    t.x = h * (a7.y - a7.x); t.y = -h * (a7.x + a7.y); a7 = t;
-  }
+  a5 = mul_cs<DIR>(a5, h, h);
   a6 = mul_i<DIR>(a6);
+  a7 = mul_cs<DIR>(a7, -h, h);
   T2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = mul_i<DIR>(csub(a1, a3));
   T2 b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = mul_i<DIR>(csub(a5, a7));
   v[0] = cadd(b0, b1); v[4] = csub(b0, b1);
@@ -122,142 +132,204 @@ __device__ __forceinline__ void bfly8(T2 (&v)[8]) {
   v[3] = cadd(b6, b7); v[7] = csub(b6, b7);
 }
 
+// 16-point DFT as 4 x 4.  Input natural order v[n]; the result X[m] is left at
+// v[4*(m&3) + (m>>2)] (use out16(m)); the transposition is resolved at compile time.
+__host__ __device__ constexpr int out16(int m) { return 4 * (m & 3) + (m >> 2); }
+
+template <int DIR, typename T2>
+__device__ __forceinline__ void dft16(T2 *v) {
+  typedef decltype(v[0].x) T;
+  const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
+  // X[k1 + 4 k2] = sum_n2 w16^{n2 k1} ( sum_n1 x[4 n1 + n2] w4^{n1 k1} ) w4^{n2 k2}
+#pragma unroll
+  for (int n2 = 0; n2 < 4; n2++) dft4<DIR>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);  // -> v[4 k1 + n2]
+  // twiddles w16^{n2 k1}
+  v[5] = mul_cs<DIR>(v[5], c1, s1);    // k1=1,n2=1 : w^1
+  v[6] = mul_cs<DIR>(v[6], h, h);      // k1=1,n2=2 : w^2
+  v[7] = mul_cs<DIR>(v[7], s1, c1);    // k1=1,n2=3 : w^3
+  v[9] = mul_cs<DIR>(v[9], h, h);      // k1=2,n2=1 : w^2
+  v[10] = mul_i<DIR>(v[10]);           // k1=2,n2=2 : w^4
+  v[11] = mul_cs<DIR>(v[11], -h, h);   // k1=2,n2=3 : w^6
+  v[13] = mul_cs<DIR>(v[13], s1, c1);  // k1=3,n2=1 : w^3
+  v[14] = mul_cs<DIR>(v[14], -h, h);   // k1=3,n2=2 : w^6
+  v[15] = mul_cs<DIR>(v[15], -c1, -s1);  // k1=3,n2=3 : w^9 = -w^1
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) dft4<DIR>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);  // -> v[4 k1 + k2]
+}
+
 // barrier over the threads of one transform: id 0 = the whole CTA (__syncthreads), id 1..15 = a
 // named barrier shared by the `count` threads working on this transform, so that independent
-// transforms in one CTA do not wait for each other
+// transforms in one CTA do not wait for each other (count must be a multiple of 32)
 __device__ __forceinline__ void fft_sync(int bar, int count) {
   if (bar == 0) __syncthreads();
   else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(count) : "memory");
 }
 
-// compile-time stage plan of a length-L transform: radix 8 while possible, then 4 or 2
 template <int L>
-struct Plan {
-  // number of first-order twiddles a unit needs over all stages with Ns > 1
-  template <int Ns>
-  static constexpr int count() {
-    constexpr int rem = L / Ns;
-    if constexpr (rem >= 8) return (Ns > 1 ? 1 : 0) + count<Ns * 8>();
-    else if constexpr (rem == 4) return 2;
-    else if constexpr (rem == 2) return 4;
-    else return 0;
+struct Plan16 {
+  static constexpr int log2() {
+    int n = 0, l = L;
+    while (l > 1) { l >>= 1; n++; }
+    return n;
   }
-  static constexpr int NW = count<1>();
+  static constexpr int N16 = log2() / 4;             // radix-16 stages
+  static constexpr int REM = 1 << (log2() % 4);     // radix of the final stage (1 = none)
+  static constexpr int QREM = REM > 1 ? 16 / REM : 0;
+  // first-order twiddles per thread: one per radix-16 stage after the first, QREM for the final stage
+  static constexpr int NW = (N16 > 1 ? N16 - 1 : 0) + (N16 > 0 ? QREM : 0);
 };
 
-// In-place shared-memory FFT of length L executed by NT = L/8/BPT threads per transform
-// (thread index t in [0,NT)); every thread of the CTA must call run() (it contains
-// __syncthreads()).  The caller fills s[pad(e)] (natural order), synchronises, calls run();
-// on return (after a final barrier) s[pad(f)] holds the transform in natural order.
-template <typename T, int L, int BPT>
+// default functors: plain padded shared-memory access
+// default functors: plain padded shared-memory access.  A thread's first-stage inputs and its
+// last-stage outputs are both the elements u + m*NT, m = 0..15; m is passed to the functors as
+// a compile-time-constant (after unrolling) register index.
+template <typename T2>
+struct SmemLoad {
+  const T2 *s;
+  __device__ __forceinline__ T2 operator()(int e, int /*m*/) const { return s[pad(e)]; }
+};
+template <typename T2>
+struct SmemStore {
+  T2 *s;
+  __device__ __forceinline__ void operator()(int f, T2 v, int /*m*/) const { s[pad(f)] = v; }
+};
+
+// FFT of length L in shared memory `s` (padded_size(L) elements) by NT = L/16 threads, thread
+// index u in [0, NT).  Every thread of the barrier group must call run().
+//   LoadOp  ld(e, m)    -> input element e = u + m*NT (natural order) of the first stage
+//   StoreOp st(f, v, m) -> consumes output element f = u + m*NT (natural order) of the last stage
+// IN_SMEM : the first stage reads shared memory that other threads of the group may still be
+//           writing/reading -> the caller must have synchronised; also tells the engine that a
+//           barrier is needed between the first stage's reads and its writes.
+// OUT_SMEM: the StoreOp writes the transform's own buffer `s` -> a final barrier is issued.
+template <typename T, int L>
 struct BlockFFT {
   typedef typename V2<T>::type T2;
-  static constexpr int UNITS = L / 8;
-  static constexpr int NT = UNITS / BPT;
-  static constexpr int NW = Plan<L>::NW * BPT;
-  static_assert(L >= 8 && (L & (L - 1)) == 0, "L must be a power of two >= 8");
-  static_assert(UNITS % BPT == 0, "BPT must divide L/8");
+  typedef Plan16<L> P;
+  static constexpr int NT = L / 16;
+  static constexpr int NW = P::NW;
+  static_assert(L >= 32 && (L & (L - 1)) == 0, "L must be a power of two >= 32");
 
-  // per-thread first-order (forward) twiddles of every stage, held in registers
   struct Twiddles {
     T2 w[NW > 0 ? NW : 1];
-
-    template <int Ns, int OFF>
-    __device__ __forceinline__ void fill(const T2 *__restrict__ tw, int tw_stride, int t) {
-      constexpr int rem = L / Ns;
-      constexpr int R = rem >= 8 ? 8 : rem;
-      constexpr int Q = 8 / R;
-      if constexpr (rem >= 2) {
-        if constexpr (Ns > 1) {
+    // tw: table exp(-2 pi i j / (L*tw_stride)), j < L*tw_stride
+    __device__ __forceinline__ void init(const T2 *__restrict__ tw, int tw_stride, int u) {
+      int o = 0;
+      int Ns = 16;
 #pragma unroll
-          for (int b = 0; b < BPT; b++)
-#pragma unroll
-            for (int q = 0; q < Q; q++) {
-              const int j = t + b * NT + q * UNITS;
-              const int k = j & (Ns - 1);
-              w[OFF + b * Q + q] = tw[k * (L / (Ns * R)) * tw_stride];
-            }
-        }
-        // another stage follows only after a radix-8 stage that leaves a remainder
-        if constexpr (rem >= 16) fill<Ns * 8, OFF + (Ns > 1 ? BPT : 0)>(tw, tw_stride, t);
+      for (int st = 1; st < P::N16; st++) {  // radix-16 stages after the first: j = u
+        const int k = u & (Ns - 1);
+        w[o++] = tw[k * (L / (Ns * 16)) * tw_stride];
+        Ns *= 16;
       }
-    }
-    // tw: table exp(-2 pi i j / (L*tw_stride))
-    __device__ __forceinline__ void init(const T2 *__restrict__ tw, int tw_stride, int t) {
-      fill<1, 0>(tw, tw_stride, t);
+      if (P::REM > 1) {
+#pragma unroll
+        for (int q = 0; q < P::QREM; q++) {
+          const int j = u + q * NT;
+          const int k = j & (Ns - 1);
+          w[o++] = tw[k * (L / (Ns * P::REM)) * tw_stride];
+        }
+      }
     }
   };
 
-  // one Stockham stage of radix R with Ns = product of the previous radices
-  template <int DIR, int R, int Ns, int OFF>
-  static __device__ __forceinline__ void stage(T2 *__restrict__ s, const Twiddles &tws, int t, int bar) {
-    constexpr int Q = 8 / R;  // radix-R butterflies per unit
-    T2 v[BPT][8];
-#pragma unroll
-    for (int b = 0; b < BPT; b++) {
-      const int u = t + b * NT;
-#pragma unroll
-      for (int q = 0; q < Q; q++) {
-        const int j = u + q * UNITS;
-#pragma unroll
-        for (int r = 0; r < R; r++) v[b][q * R + r] = s[pad(j + r * (L / R))];
-        if (Ns > 1) {
-          T2 w1 = tws.w[OFF + b * Q + q];
-          if (DIR > 0) w1.y = -w1.y;
-          T2 *x = &v[b][q * R];
-          x[1] = cmul(x[1], w1);
-          if (R >= 4) {
-            T2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
-            x[2] = cmul(x[2], w2);
-            x[3] = cmul(x[3], w3);
-            if (R == 8) {
-              T2 w4 = cmul(w2, w2);
-              x[4] = cmul(x[4], w4);
-              x[5] = cmul(x[5], cmul(w4, w1));
-              x[6] = cmul(x[6], cmul(w3, w3));
-              x[7] = cmul(x[7], cmul(w4, w3));
-            }
-          }
+  // multiply x[1..R-1] by w^1..w^(R-1)
+  template <int DIR, int R>
+  static __device__ __forceinline__ void apply_twiddles(T2 *x, T2 w1) {
+    if (DIR > 0) w1.y = -w1.y;
+    x[1] = cmul(x[1], w1);
+    if (R >= 4) {
+      T2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+      x[2] = cmul(x[2], w2);
+      x[3] = cmul(x[3], w3);
+      if (R >= 8) {
+        T2 w4 = cmul(w2, w2);
+        x[4] = cmul(x[4], w4);
+        x[5] = cmul(x[5], cmul(w4, w1));
+        x[6] = cmul(x[6], cmul(w3, w3));
+        T2 w7 = cmul(w4, w3);
+        x[7] = cmul(x[7], w7);
+        if (R == 16) {
+          T2 w8 = cmul(w4, w4);
+          x[8] = cmul(x[8], w8);
+          x[9] = cmul(x[9], cmul(w8, w1));
+          x[10] = cmul(x[10], cmul(w8, w2));
+          x[11] = cmul(x[11], cmul(w8, w3));
+          x[12] = cmul(x[12], cmul(w8, w4));
+          x[13] = cmul(x[13], cmul(w7, cmul(w3, w3)));
+          x[14] = cmul(x[14], cmul(w7, w7));
+          x[15] = cmul(x[15], cmul(w8, w7));
         }
       }
-      if (R == 8) bfly8<DIR>(v[b]);
-      if (R == 4) { bfly4<DIR>(v[b], 0); bfly4<DIR>(v[b], 4); }
-      if (R == 2) { bfly2<DIR>(v[b], 0); bfly2<DIR>(v[b], 2); bfly2<DIR>(v[b], 4); bfly2<DIR>(v[b], 6); }
     }
-    fft_sync(bar, NT);
+  }
+
+  // one Stockham stage of radix R (Q = 16/R butterflies per unit), Ns = product of previous radices
+  template <int DIR, int R, int Ns, int WOFF, bool FIRST, bool LAST, bool SYNC_BEFORE_WRITE, bool SYNC_AFTER_WRITE,
+            class LoadOp, class StoreOp>
+  static __device__ __forceinline__ void stage(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
+                                               const StoreOp &st) {
+    constexpr int Q = 16 / R;
+    T2 v[16];
 #pragma unroll
-    for (int b = 0; b < BPT; b++) {
-      const int u = t + b * NT;
+    for (int q = 0; q < Q; q++) {
 #pragma unroll
-      for (int q = 0; q < Q; q++) {
-        const int j = u + q * UNITS;
-        const int k = j & (Ns - 1);
-        const int d = (j - k) * R + k;
+      for (int r = 0; r < R; r++) {
+        const int e = u + (q + r * Q) * NT;  // = j + r*L/R with j = u + q*NT
+        v[q * R + r] = FIRST ? ld(e, q + r * Q) : s[pad(e)];
+      }
+      if (Ns > 1) apply_twiddles<DIR, R>(&v[q * R], tws.w[WOFF + q]);
+      if (R == 16) dft16<DIR>(&v[0]);
+      if (R == 8) dft8<DIR>(&v[q * 8]);
+      if (R == 4) dft4<DIR>(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      if (R == 2) dft2<DIR>(v[q * 2], v[q * 2 + 1]);
+    }
+    if (SYNC_BEFORE_WRITE) fft_sync(bar, NT);
 #pragma unroll
-        for (int r = 0; r < R; r++) s[pad(d + r * Ns)] = v[b][q * R + r];
+    for (int q = 0; q < Q; q++) {
+      const int j = u + q * NT;
+      const int k = j & (Ns - 1);
+      const int d = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const T2 val = v[q * R + (R == 16 ? out16(r) : r)];
+        if (LAST) st(d + r * Ns, val, q + r * Q);  // here Ns = L/R, so d + r*Ns = u + (q + r*Q)*NT
+        else s[pad(d + r * Ns)] = val;
       }
     }
-    fft_sync(bar, NT);
+    if (SYNC_AFTER_WRITE) fft_sync(bar, NT);
   }
 
-  template <int DIR, int Ns, int OFF>
-  static __device__ __forceinline__ void from(T2 *__restrict__ s, const Twiddles &tws, int t, int bar) {
+  template <int DIR, int I, int Ns, bool IN_SMEM, bool OUT_SMEM, class LoadOp, class StoreOp>
+  static __device__ __forceinline__ void from(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
+                                              const StoreOp &st) {
     constexpr int rem = L / Ns;
-    if constexpr (rem >= 8) {
-      stage<DIR, 8, Ns, OFF>(s, tws, t, bar);
-      from<DIR, Ns * 8, OFF + (Ns > 1 ? BPT : 0)>(s, tws, t, bar);
-    } else if constexpr (rem == 4) {
-      stage<DIR, 4, Ns, OFF>(s, tws, t, bar);
-    } else if constexpr (rem == 2) {
-      stage<DIR, 2, Ns, OFF>(s, tws, t, bar);
+    constexpr bool first = (I == 0);
+    // the reads of a stage must complete before its writes unless the reads did not touch smem
+    constexpr bool sync_bw = first ? IN_SMEM : true;
+    if constexpr (rem >= 16) {
+      constexpr bool last = (rem == 16);
+      constexpr bool sync_aw = last ? OUT_SMEM : true;
+      // when the last stage does not write smem nobody waits for its reads either
+      stage<DIR, 16, Ns, (I > 0 ? I - 1 : 0), first, last, (last && !OUT_SMEM) ? false : sync_bw, sync_aw>(s, tws, u, bar, ld, st);
+      if constexpr (!last) from<DIR, I + 1, Ns * 16, IN_SMEM, OUT_SMEM>(s, tws, u, bar, ld, st);
+    } else if constexpr (rem > 1) {
+      stage<DIR, rem, Ns, (P::N16 > 1 ? P::N16 - 1 : 0), first, true, OUT_SMEM ? sync_bw : false, OUT_SMEM>(s, tws, u, bar, ld, st);
     }
   }
 
-  // bar: see fft_sync.  The caller must have made its writes to s visible to the NT threads
-  // of this transform (same barrier) before calling.
+  template <int DIR, bool IN_SMEM, bool OUT_SMEM, class LoadOp, class StoreOp>
+  static __device__ __forceinline__ void run(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
+                                             const StoreOp &st) {
+    from<DIR, 0, 1, IN_SMEM, OUT_SMEM>(s, tws, u, bar, ld, st);
+  }
+
+  // plain in-place transform of s (input already in s and synchronised; output in s, synchronised)
   template <int DIR>
-  static __device__ __forceinline__ void run(T2 *__restrict__ s, const Twiddles &tws, int t, int bar = 0) {
-    from<DIR, 1, 0>(s, tws, t, bar);
+  static __device__ __forceinline__ void run_inplace(T2 *__restrict__ s, const Twiddles &tws, int u, int bar) {
+    SmemLoad<T2> ld{s};
+    SmemStore<T2> st{s};
+    run<DIR, true, true>(s, tws, u, bar, ld, st);
   }
 };
 

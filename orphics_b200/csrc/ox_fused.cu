@@ -1,23 +1,26 @@
 // Fused hand-written path for sim -> FFT -> power2d -> bin2D on power-of-two maps.
 //
 // cuFFT's 2-D real transforms run at ~50% of their own two-pass HBM bound on B200
-// (40 us per 2048^2 fp64 transform), which alone would cap the pipeline at ~40% of its
-// roofline.  Here the four 1-D FFT passes are hand-written (ox_fft.cuh, shared-memory
-// Stockham radix-8) and fused with their producers and consumers, so a map costs three
-// kernels and ~4.s.N bytes of HBM traffic instead of ten passes:
+// (40 us per 2048^2 fp64 transform; tools/ubench/fft_layouts.cu), which alone caps the
+// pipeline at ~40% of its roofline.  Here the four 1-D FFT passes are hand-written
+// (ox_fft.cuh: register-resident radix-16 Stockham stages exchanging through shared memory)
+// and fused with their producers and consumers, so a map costs three kernels and ~4.s.N
+// bytes of HBM traffic instead of ten passes:
 //
-//   K_A fused_sim_col : Philox/Box-Muller noise x covsqrt [x EB->QU] -> Hermitian k_h
-//                        generated straight into shared memory -> inverse FFT along y ->
-//                        written TRANSPOSED Ht[ix][y] (contiguous, coalesced)
-//   K_B fused_row     : tile of R rows: c2r inverse FFT along x (half-length complex FFT
-//                        + Hermitian packing) -> real map (optionally stored) x taper ->
-//                        r2c forward FFT along x -> written transposed Ht'[ix][y]
-//   K_C fused_col_bin : forward FFT along y of each column -> [QU->EB] -> conj(k_i) k_j ->
-//                        deterministic annular binning (warp-private slots, reduce_peers)
+//   K_A fused_sim_col : Philox/Box-Muller noise x covsqrt [x EB->QU] -> Hermitian k_h written
+//                        to shared memory -> inverse FFT along y -> last stage stores straight
+//                        to HBM, TRANSPOSED: Ht[ix][y] (contiguous, coalesced)
+//   K_B fused_row     : tile of R rows: Hermitian packing fused into the first stage of the
+//                        half-length inverse FFT along x -> last stage multiplies by the taper
+//                        (and optionally stores the real map) -> forward FFT -> unpacking fused
+//                        into the transposed store Ht'[ix][y]
+//   K_C fused_col_bin : first stage loads a column from HBM -> forward FFT along y -> last stage
+//                        feeds |k|^2 straight into the deterministic annular binning
+//                        (T-only) or via shared memory for the six TEB spectra
 //
 // The intermediate layout is the half plane transposed, [plane][ix = 0..Nx/2][iy = 0..Ny),
 // so K_A writes and K_C reads whole columns contiguously and only K_B touches R x 16 B
-// segments (R = 4 or 8 rows -> 64/128 B, sector aligned).
+// segments (R = 4 rows -> 64 B, sector aligned).
 #include <math.h>
 
 #include "ox_common.cuh"
@@ -68,6 +71,17 @@ __device__ __forceinline__ void rot_cs(double y, double x, double sgn, double &c
   }
 }
 
+// asynchronous global -> shared copy of one element (LDGSTS): no register staging
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// deterministic in-warp reduce-by-key: afterwards the lowest lane of every group of equal keys
+// holds the group's sums (fixed shuffle tree, see ox_binner.cu)
 template <int NV>
 __device__ __forceinline__ void reduce_peers(unsigned peers, double (&v)[NV]) {
   const int lane = threadIdx.x & 31;
@@ -94,18 +108,24 @@ struct SimColArgs {
   const double *noise;     // host-noise mode: [nsim][2][NC][ny][nx] natural layout
   const long long *seeds;  // [nsim]
   const double *ly, *lx;
-  const typename V2<T>::type *tw;  // exp(-2 pi i j / LT)
+  const typename V2<T>::type *tw;  // exp(-2 pi i j / tw_len)
   int tw_len;
   int ny, nx, mx;  // mx = nx/2
   int mode, rot, cov_symmetric;
   double scale, rot_sgn;
 };
 
-template <typename T, int LY, int NC, int BPT>
-__global__ void __launch_bounds__(NC *(LY / 8 / BPT))
+template <typename T2>
+struct GlobalStore {
+  T2 *dst;
+  __device__ __forceinline__ void operator()(int f, T2 v, int) const { dst[f] = v; }
+};
+
+template <typename T, int LY, int NC>
+__global__ void __launch_bounds__(NC *(LY / 16))
 fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[nsim][NC][mx+1][ny]*/) {
   typedef typename V2<T>::type T2;
-  typedef BlockFFT<T, LY, BPT> FFT;
+  typedef BlockFFT<T, LY> FFT;
   constexpr int NT = FFT::NT, NTHREADS = NC * NT, PS = padded_size(LY);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T2 *s = reinterpret_cast<T2 *>(smem_raw);  // [NC][PS]
@@ -114,6 +134,7 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
   const long long n = (long long)a.ny * a.nx;
   const unsigned long long seed = a.mode == OX_NOISE_HOST ? 0ull : (unsigned long long)a.seeds[sim];
   const double h = 0.5 * a.scale;
+#pragma unroll 1
   for (int iy = tid; iy < LY; iy += NTHREADS) {
     const int my = iy ? a.ny - iy : 0;
     const long long p = (long long)iy * a.nx + ix, q = (long long)my * a.nx + mxp;
@@ -172,6 +193,7 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
       kpr[i] = sr; kpi[i] = si; kqr[i] = ur; kqi[i] = ui;
     }
     if (NC == 3 && a.rot) {
+      // inverse queb_rotmat: [Q;U] = [[c, s],[-s, c]] [E;B], each pixel with its own angle
       double c, sn;
       rot_cs(a.ly[iy], a.lx[ix], a.rot_sgn, c, sn);
       double t1 = c * kpr[1] + sn * kpr[2], t2 = c * kpi[1] + sn * kpi[2];
@@ -191,17 +213,13 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
     }
   }
   __syncthreads();
-  const int f = tid / NT, t = tid - f * NT;
-  {
-    typename FFT::Twiddles tws;
-    tws.init(a.tw, a.tw_len / LY, t);
-    FFT::template run<+1>(s + f * PS, tws, t);
-  }
-  T2 *out = Ht + ((long long)sim * NC * (a.mx + 1) + ix) * a.ny;
-  for (int e = tid; e < NC * LY; e += NTHREADS) {
-    int c = e / LY, iy = e - c * LY;
-    out[(long long)c * (a.mx + 1) * a.ny + iy] = s[c * PS + pad(iy)];
-  }
+  const int f = tid / NT, u = tid - f * NT;
+  typename FFT::Twiddles tws;
+  tws.init(a.tw, a.tw_len / LY, u);
+  const int bar = (NC > 1 && NT % 32 == 0) ? 1 + f : 0;
+  SmemLoad<T2> ld{s + f * PS};
+  GlobalStore<T2> st{Ht + (((long long)sim * NC + f) * (a.mx + 1) + ix) * a.ny};
+  FFT::template run<+1, true, false>(s + f * PS, tws, u, bar, ld, st);
 }
 
 // ---- K_B -------------------------------------------------------------------------------
@@ -217,98 +235,100 @@ struct RowArgs {
   int ny, nx, mx;
 };
 
-// R rows per CTA, each a length-MX complex FFT handled by NT threads
-template <typename T, int MX, int R, int BPT>
-__global__ void __launch_bounds__(R *(MX / 8 / BPT), (R * (MX / 8 / BPT) <= 512 ? 2 : 1))
+// first-stage input of the c2r transform: Z[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/Nx} (X[k] - conj X[M-k])
+template <typename T2, int MX>
+struct PackLoad {
+  const T2 *row;  // X[0..MX] in padded shared memory
+  const T2 *tw;   // exp(-2 pi i j / tw_len)
+  int tws_n;      // tw_len / Nx
+  __device__ __forceinline__ T2 operator()(int k, int) const {
+    T2 xk = row[pad(k)], xm = row[pad(MX - k)];
+    T2 w = tw[k * tws_n];
+    w.y = -w.y;
+    T2 sum = cadd(xk, cconj(xm)), dif = csub(xk, cconj(xm));
+    return cadd(sum, mul_i<+1>(cmul(w, dif)));
+  }
+};
+
+// last-stage output of the c2r transform: z[n] = x[2n] + i x[2n+1]; store the map, apply the taper
+template <typename T, int MX>
+struct WindowStore {
+  typedef typename V2<T>::type T2;
+  T2 *row;           // shared
+  T2 *map_row;       // global or null
+  const T2 *win_row; // global or null
+  __device__ __forceinline__ void operator()(int n, T2 z, int) const {
+    if (map_row) map_row[n] = z;
+    if (win_row) {
+      T2 w = win_row[n];
+      z.x *= w.x;
+      z.y *= w.y;
+    }
+    row[pad(n)] = z;
+  }
+};
+
+// R rows per CTA, each a length-MX complex FFT handled by NT = MX/16 threads
+template <typename T, int MX, int R>
+__global__ void __launch_bounds__(R *(MX / 16), (R * (MX / 16) <= 256 ? 2 : 1))
 fused_row_kernel(RowArgs<T> a) {
   typedef typename V2<T>::type T2;
-  typedef BlockFFT<T, MX, BPT> FFT;
+  typedef BlockFFT<T, MX> FFT;
   constexpr int NT = FFT::NT, NTHREADS = R * NT, PS = padded_size(MX), NX = 2 * MX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T2 *s = reinterpret_cast<T2 *>(smem_raw);  // [R][PS]
   const int tid = threadIdx.x;
   const int iy0 = blockIdx.x * R;
   const long long plane = blockIdx.y;
-  const int f = tid / NT, t = tid - f * NT;
+  const int f = tid / NT, u = tid - f * NT;
   T2 *row = s + f * PS;
   const int tws_n = a.tw_len / NX;  // stride for exp(-2 pi i k / Nx)
   typename FFT::Twiddles tws;
-  tws.init(a.tw, a.tw_len / MX, t);
+  tws.init(a.tw, a.tw_len / MX, u);
   // the NT threads of one row synchronise among themselves only (named barriers need whole warps)
   const int bar = (NT % 32 == 0) ? 1 + f : 0;
+  const long long rowoff = (long long)(iy0 + f) * MX;
+  WindowStore<T, MX> wst;
+  wst.row = row;
+  wst.map_row = a.map_out ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
+  wst.win_row = a.window ? reinterpret_cast<const T2 *>(a.window) + rowoff : nullptr;
   if (a.Hin) {
     // tile load: for each ix the R rows are R*16 B contiguous in the transposed layout
     const T2 *src = a.Hin + plane * (long long)(MX + 1) * a.ny + iy0;
     for (int e = tid; e < (MX + 1) * R; e += NTHREADS) {
       int ix = e / R, r = e - ix * R;
-      s[r * PS + pad(ix)] = src[(long long)ix * a.ny + r];
+      cp_async<sizeof(T2)>(&s[r * PS + pad(ix)], &src[(long long)ix * a.ny + r]);
     }
+    cp_async_wait_all();
     __syncthreads();
-    // Hermitian packing: Z[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/Nx} (X[k] - conj X[M-k])
-    for (int k = t; k <= MX / 2; k += NT) {
-      const int km = MX - k;
-      T2 xk = row[pad(k)], xm = row[pad(km)];
-      T2 w = a.tw[k * tws_n];
-      w.y = -w.y;  // e^{+2 pi i k/Nx}
-      T2 sum = cadd(xk, cconj(xm)), dif = csub(xk, cconj(xm));
-      T2 wd = mul_i<+1>(cmul(w, dif));
-      T2 zk = cadd(sum, wd);
-      // Z[M-k] = conj(sum) + i e^{+2 pi i (M-k)/Nx} (X[M-k] - conj X[k]) ; e^{2 pi i (M-k)/Nx} = -conj(w)
-      T2 zm = csub(cconj(sum), cconj(wd));
-      if (k == 0) {
-        row[pad(0)] = zk;  // X[M] consumed; slot M no longer needed
-      } else {
-        row[pad(k)] = zk;
-        if (km != k) row[pad(km)] = zm;
-      }
-    }
-    fft_sync(bar, NT);
-    FFT::template run<+1>(row, tws, t, bar);
-    // row[n] = x[2n] + i x[2n+1]
+    PackLoad<T2, MX> ld{row, a.tw, tws_n};
+    FFT::template run<+1, true, true>(row, tws, u, bar, ld, wst);
   } else {
-    const T2 *src = reinterpret_cast<const T2 *>(a.map_in + (plane * a.ny + iy0) * (long long)NX);
-    for (int e = tid; e < MX * R; e += NTHREADS) {
-      int r = e / MX, n = e - r * MX;
-      s[r * PS + pad(n)] = src[(long long)r * MX + n];
-    }
-    __syncthreads();
-  }
-  if (a.map_out || a.window) {
-    // each row's threads handle their own row (no CTA-wide barrier needed)
-    const long long rowoff = (long long)(iy0 + f) * MX;
-    for (int n = t; n < MX; n += NT) {
-      T2 z = row[pad(n)];
-      if (a.map_out) reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX)[rowoff + n] = z;
-      if (a.window) {
-        T2 w = reinterpret_cast<const T2 *>(a.window)[rowoff + n];
-        z.x *= w.x;
-        z.y *= w.y;
-        row[pad(n)] = z;
-      }
+    // real map rows viewed as z[n] = x[2n] + i x[2n+1]
+    const T2 *src = reinterpret_cast<const T2 *>(a.map_in + (plane * a.ny + iy0 + f) * (long long)NX);
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      const int n = u + m * NT;
+      wst(n, src[n], m);
     }
     fft_sync(bar, NT);
   }
   if (!a.Hout) return;
-  FFT::template run<-1>(row, tws, t, bar);
-  // unpack: X[k] = 1/2 [(Z[k] + conj Z[M-k]) - i e^{-2 pi i k/Nx} (Z[k] - conj Z[M-k])], k = 0..M
-  for (int k = t; k <= MX / 2; k += NT) {
-    const int km = MX - k;
-    T2 zk = row[pad(k)], zm = (k == 0) ? zk : row[pad(km)];
-    T2 w = a.tw[k * tws_n];  // e^{-2 pi i k/Nx}
-    T2 sum = cadd(zk, cconj(zm)), dif = csub(zk, cconj(zm));
-    T2 wd = mul_i<-1>(cmul(w, dif));
-    T2 xk = cadd(sum, wd);
-    // X[M-k] = 1/2 [conj(sum) - i e^{-2 pi i (M-k)/Nx} (Z[M-k] - conj Z[k])] ; the phase is -conj(w)
-    T2 xm = csub(cconj(sum), cconj(wd));
-    xk.x *= (T)0.5; xk.y *= (T)0.5; xm.x *= (T)0.5; xm.y *= (T)0.5;
-    row[pad(k)] = xk;
-    if (km != k) row[pad(km)] = xm;
-  }
+  FFT::template run_inplace<-1>(row, tws, u, bar);
   __syncthreads();
+  // transposed store with the r2c unpacking fused in:
+  // X[k] = 1/2 [(Z[k] + conj Z[M-k]) - i e^{-2 pi i k/Nx} (Z[k] - conj Z[M-k])], k = 0..M, Z[M] = Z[0]
   T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + iy0;
   for (int e = tid; e < (MX + 1) * R; e += NTHREADS) {
-    int ix = e / R, r = e - ix * R;
-    dst[(long long)ix * a.ny + r] = s[r * PS + pad(ix)];
+    int k = e / R, r = e - k * R;
+    const T2 *zr = s + r * PS;
+    T2 zk = zr[pad(k == MX ? 0 : k)], zm = zr[pad(k == 0 ? 0 : MX - k)];
+    T2 w = a.tw[k * tws_n];
+    T2 sum = cadd(zk, cconj(zm)), dif = csub(zk, cconj(zm));
+    T2 x = cadd(sum, mul_i<-1>(cmul(w, dif)));
+    x.x *= (T)0.5;
+    x.y *= (T)0.5;
+    dst[(long long)k * a.ny + r] = x;
   }
 }
 
@@ -324,11 +344,43 @@ struct ColBinArgs {
   double rot_sgn;
 };
 
-template <typename T, int LY, int NC, int BPT>
-__global__ void __launch_bounds__(NC *(LY / 8 / BPT))
+template <typename T2>
+struct GlobalLoad {
+  const T2 *src;
+  __device__ __forceinline__ T2 operator()(int e, int) const { return src[e]; }
+};
+
+// last stage of the T-only column transform: |k|^2 x Hermitian weight straight into the
+// warp-private slot sums.  Slots 0 (at/below the first edge) and nslots-1 (above the last edge)
+// are dropped by bin2D's [1:-1] (stats.py:796-797): nothing is accumulated for them.
+template <typename T2>
+struct BinStore {
+  const unsigned short (&raws)[16];
+  double *mine;
+  unsigned trash, last;
+  int lane;
+  __device__ __forceinline__ BinStore(const unsigned short (&r)[16], double *m, unsigned t, unsigned l, int ln)
+      : raws(r), mine(m), trash(t), last(l), lane(ln) {}
+  __device__ __forceinline__ void operator()(int, T2 z, int m) const {
+    const unsigned raw = raws[m];
+    unsigned key = raw & 0x7fffu;
+    if (key == 0u || key == last) key = trash;
+    if (__all_sync(0xffffffffu, key == trash)) return;
+    double v[1];
+    v[0] = key != trash ? ((double)z.x * (double)z.x + (double)z.y * (double)z.y) * ((raw & 0x8000u) ? 2.0 : 1.0) : 0.0;
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    bool leader = (__ffs(peers) - 1) == lane;
+    reduce_peers<1>(peers, v);
+    if (leader) mine[key] += v[0];
+    __syncwarp();
+  }
+};
+
+template <typename T, int LY, int NC>
+__global__ void __launch_bounds__(NC *(LY / 16))
 fused_col_bin_kernel(ColBinArgs<T> a, double *__restrict__ partial /*[nbatch][gridDim.x][NS][nslots]*/) {
   typedef typename V2<T>::type T2;
-  typedef BlockFFT<T, LY, BPT> FFT;
+  typedef BlockFFT<T, LY> FFT;
   constexpr int NT = FFT::NT, NTHREADS = NC * NT, PS = padded_size(LY), NS = NC * (NC + 1) / 2, NWARPS = NTHREADS / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T2 *s = reinterpret_cast<T2 *>(smem_raw);                                           // [NC][PS]
@@ -338,79 +390,69 @@ fused_col_bin_kernel(ColBinArgs<T> a, double *__restrict__ partial /*[nbatch][gr
   double *mine = bins + (size_t)warp * NS * stride;
   for (int i = lane; i < NS * stride; i += 32) mine[i] = 0.0;
   const long long b = blockIdx.y;
-  const int f = tid / NT, t = tid - f * NT;
+  const int f = tid / NT, u = tid - f * NT;
   const int ix0 = blockIdx.x * a.cols_per_block;
   const int ix1 = min(ix0 + a.cols_per_block, a.mx + 1);
   typename FFT::Twiddles tws;
-  tws.init(a.tw, a.tw_len / LY, t);
-  // software pipeline: the next column is fetched into registers while this one is transformed and binned
-  constexpr int EPT = NC * LY / NTHREADS;  // elements per thread (8 * BPT)
-  T2 pre[EPT];
-  {
-    const T2 *src = a.H + (b * NC * (a.mx + 1) + ix0) * (long long)a.ny;
-#pragma unroll
-    for (int i = 0; i < EPT; i++) {
-      int e = tid + i * NTHREADS, c = e / LY, iy = e - c * LY;
-      pre[i] = src[(long long)c * (a.mx + 1) * a.ny + iy];
-    }
-  }
+  tws.init(a.tw, a.tw_len / LY, u);
+  const unsigned trash = a.nslots, last = a.nslots - 1;
+  const int bar = (NC > 1 && NT % 32 == 0) ? 1 + f : 0;
   for (int ix = ix0; ix < ix1; ix++) {
-    __syncthreads();  // previous column's readers are done with s
-#pragma unroll
-    for (int i = 0; i < EPT; i++) {
-      int e = tid + i * NTHREADS, c = e / LY, iy = e - c * LY;
-      s[c * PS + pad(iy)] = pre[i];
-    }
-    if (ix + 1 < ix1) {
-      const T2 *src = a.H + (b * NC * (a.mx + 1) + ix + 1) * (long long)a.ny;
-#pragma unroll
-      for (int i = 0; i < EPT; i++) {
-        int e = tid + i * NTHREADS, c = e / LY, iy = e - c * LY;
-        pre[i] = src[(long long)c * (a.mx + 1) * a.ny + iy];
-      }
-    }
-    __syncthreads();
-    FFT::template run<-1>(s + f * PS, tws, t);
     const uint16_t *idx = a.idxT + (long long)ix * a.ny;
-    const double x = a.lx[ix];
-    for (int base = 0; base < LY; base += NTHREADS) {
-      const int iy = base + tid;
-      unsigned key = a.nslots;
-      double v[NS];
+    GlobalLoad<T2> ld{a.H + ((b * NC + f) * (a.mx + 1) + ix) * (long long)a.ny};
+    __syncthreads();  // the previous column's readers are done with s
+    if (NC == 1) {
+      // slot indices of this thread's 16 outputs (u + m*NT), fetched before the transform
+      unsigned short raws[16];
 #pragma unroll
-      for (int q = 0; q < NS; q++) v[q] = 0.0;
-      if (iy < LY) {
-        unsigned raw = idx[iy];
-        key = raw & 0x7fffu;
-        const double w = (raw & 0x8000u) ? 2.0 : 1.0;
-        double re[NC], im[NC];
+      for (int m = 0; m < 16; m++) raws[m] = idx[u + m * NT];
+      BinStore<T2> st(raws, mine, trash, last, lane);
+      FFT::template run<-1, false, false>(s, tws, u, 0, ld, st);
+    } else {
+      SmemStore<T2> st{s + f * PS};
+      FFT::template run<-1, false, true>(s + f * PS, tws, u, bar, ld, st);
+      __syncthreads();
+      const double x = a.lx[ix];
+      for (int base = 0; base < LY; base += NTHREADS) {
+        const int iy = base + tid;
+        unsigned raw = iy < LY ? idx[iy] : 0;
+        unsigned key = raw & 0x7fffu;
+        if (iy >= LY || key == 0u || key == last) key = trash;
+        if (__all_sync(0xffffffffu, key == trash)) continue;
+        double v[NS];
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-          T2 z = s[c * PS + pad(iy)];
-          re[c] = (double)z.x;
-          im[c] = (double)z.y;
+        for (int q = 0; q < NS; q++) v[q] = 0.0;
+        if (key != trash) {
+          const double w = (raw & 0x8000u) ? 2.0 : 1.0;
+          double re[NC], im[NC];
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            T2 z = s[c * PS + pad(iy)];
+            re[c] = (double)z.x;
+            im[c] = (double)z.y;
+          }
+          if (NC == 3 && a.rot) {
+            double c, sn;
+            rot_cs(a.ly[iy], x, a.rot_sgn, c, sn);
+            double er = c * re[1] - sn * re[2], ei = c * im[1] - sn * im[2];
+            double br = sn * re[1] + c * re[2], bi = sn * im[1] + c * im[2];
+            re[1] = er; im[1] = ei; re[2] = br; im[2] = bi;
+          }
+          int q = 0;
+#pragma unroll
+          for (int i2 = 0; i2 < NC; i2++)
+#pragma unroll
+            for (int j = i2; j < NC; j++) v[q++] = (re[i2] * re[j] + im[i2] * im[j]) * w;
         }
-        if (NC == 3 && a.rot) {
-          double c, sn;
-          rot_cs(a.ly[iy], x, a.rot_sgn, c, sn);
-          double er = c * re[1] - sn * re[2], ei = c * im[1] - sn * im[2];
-          double br = sn * re[1] + c * re[2], bi = sn * im[1] + c * im[2];
-          re[1] = er; im[1] = ei; re[2] = br; im[2] = bi;
+        unsigned peers = __match_any_sync(0xffffffffu, key);
+        bool leader = (__ffs(peers) - 1) == lane;
+        reduce_peers<NS>(peers, v);
+        if (leader) {
+#pragma unroll
+          for (int q = 0; q < NS; q++) mine[q * stride + key] += v[q];
         }
-        int q = 0;
-#pragma unroll
-        for (int i = 0; i < NC; i++)
-#pragma unroll
-          for (int j = i; j < NC; j++) v[q++] = (re[i] * re[j] + im[i] * im[j]) * w;
+        __syncwarp();
       }
-      unsigned peers = __match_any_sync(0xffffffffu, key);
-      bool leader = (__ffs(peers) - 1) == lane;
-      reduce_peers<NS>(peers, v);
-      if (leader) {
-#pragma unroll
-        for (int q = 0; q < NS; q++) mine[q * stride + key] += v[q];
-      }
-      __syncwarp();
     }
   }
   __syncthreads();
@@ -460,10 +502,9 @@ __global__ void transpose_idxh_kernel(const uint16_t *__restrict__ idxh, int ny,
   }
 }
 
-template <typename T2>
+// one warp per (map, spectrum, bin): lanes stride over the blocks, fixed shuffle tree
 __global__ void bandpower_finalize2_kernel(const double *__restrict__ partial, int nblk, int ns, int nslots,
                                            const double *__restrict__ count, double normfact, double *__restrict__ bp) {
-  // one warp per (map, spectrum, bin): lanes stride over the blocks, fixed shuffle tree
   const int nbins = nslots - 2;
   int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   long long m = blockIdx.y;
@@ -485,34 +526,26 @@ int set_smem(F kernel, size_t bytes) {
 
 constexpr size_t SMEM_MAX = 227 * 1024;
 
-// BPT choice: keep threads per CTA <= 512 where possible
-template <typename T, int LY, int NC>
-struct ColCfg {
-  static constexpr int BPT = (NC * (LY / 8) > 512) ? ((NC * (LY / 8) > 1024) ? 4 : 2) : 1;
-};
-
 template <typename T, int LY, int NC>
 int launch_sim_col(SimColArgs<T> &a, void *Ht, int nsim) {
-  constexpr int BPT = ColCfg<T, LY, NC>::BPT;
   typedef typename V2<T>::type T2;
   size_t smem = sizeof(T2) * NC * padded_size(LY);
   OX_REQUIRE(smem <= SMEM_MAX, "fused sim: column of %d x %d comps needs %zu B of shared memory", LY, NC, smem);
-  auto k = fused_sim_col_kernel<T, LY, NC, BPT>;
+  auto k = fused_sim_col_kernel<T, LY, NC>;
   OX_TRY(set_smem(k, smem));
   dim3 grid(a.mx + 1, nsim);
-  k<<<grid, NC * (LY / 8 / BPT), smem, g_stream>>>(a, (T2 *)Ht);
+  k<<<grid, NC * (LY / 16), smem, g_stream>>>(a, (T2 *)Ht);
   OX_KERNEL_CHECK();
   return OX_OK;
 }
 
 template <typename T, int LY, int NC>
 int launch_col_bin(ColBinArgs<T> &a, double *partial, int nbatch, int nblk) {
-  constexpr int BPT = ColCfg<T, LY, NC>::BPT;
   typedef typename V2<T>::type T2;
-  constexpr int NTHREADS = NC * (LY / 8 / BPT), NS = NC * (NC + 1) / 2;
-  size_t smem = sizeof(T2) * NC * padded_size(LY) + sizeof(double) * (NTHREADS / 32) * NS * (a.nslots + 1);
+  constexpr int NTHREADS = NC * (LY / 16), NS = NC * (NC + 1) / 2;
+  size_t smem = sizeof(T2) * NC * padded_size(LY) + sizeof(double) * ((NTHREADS + 31) / 32) * NS * (a.nslots + 1);
   OX_REQUIRE(smem <= SMEM_MAX, "fused bin: %d slots x %d spectra need %zu B of shared memory", a.nslots, NS, smem);
-  auto k = fused_col_bin_kernel<T, LY, NC, BPT>;
+  auto k = fused_col_bin_kernel<T, LY, NC>;
   OX_TRY(set_smem(k, smem));
   dim3 grid(nblk, nbatch);
   k<<<grid, NTHREADS, smem, g_stream>>>(a, partial);
@@ -520,19 +553,25 @@ int launch_col_bin(ColBinArgs<T> &a, double *partial, int nbatch, int nblk) {
   return OX_OK;
 }
 
+// rows per CTA: 64-byte segments where shared memory allows (4 x double2 / 8 x float2)
+template <typename T, int MX>
+struct RowCfg {
+  typedef typename V2<T>::type T2;
+  static constexpr int WANT = sizeof(T2) == 16 ? 4 : 8;
+  static constexpr int R = (sizeof(T2) * WANT * padded_size(MX) <= 200 * 1024) ? WANT : WANT / 2;
+};
+
 template <typename T, int MX>
 int launch_row(RowArgs<T> &a, long long nplanes) {
   typedef typename V2<T>::type T2;
-  // rows per CTA: 64-byte segments (4 x double2 / 8 x float2)
-  constexpr int R = sizeof(T2) == 16 ? 4 : 8;
-  constexpr int BPT = (R * (MX / 8) > 512) ? ((R * (MX / 8) > 1024) ? 4 : 2) : 1;
+  constexpr int R = RowCfg<T, MX>::R;
   size_t smem = sizeof(T2) * R * padded_size(MX);
   OX_REQUIRE(smem <= SMEM_MAX, "fused row: %d rows of %d need %zu B of shared memory", R, MX, smem);
   OX_REQUIRE(a.ny % R == 0, "ny must be a multiple of %d", R);
-  auto k = fused_row_kernel<T, MX, R, BPT>;
+  auto k = fused_row_kernel<T, MX, R>;
   OX_TRY(set_smem(k, smem));
   dim3 grid(a.ny / R, (unsigned)nplanes);
-  k<<<grid, R * (MX / 8 / BPT), smem, g_stream>>>(a);
+  k<<<grid, R * (MX / 16), smem, g_stream>>>(a);
   OX_KERNEL_CHECK();
   return OX_OK;
 }
@@ -546,11 +585,11 @@ namespace ox {
 
 bool fused_supported(int ny, int nx, int ncomp, int dtype) {
   if (!pow2(ny) || !pow2(nx)) return false;
-  if (ny < 256 || ny > 4096 || nx < 256 || nx > 8192) return false;
+  if (ny < 512 || ny > 4096 || nx < 256 || nx > 8192) return false;  // K_C needs whole warps: ny/16 >= 32
   if (ncomp != 1 && ncomp != 3) return false;
   size_t es = dtype == OX_F32 ? 8 : 16;
-  if (es * ncomp * padded_size(ny) + 64 * 1024 > SMEM_MAX && ncomp == 3) return false;
-  if (es * padded_size(ny) > SMEM_MAX) return false;
+  // K_A / K_C keep ncomp columns in shared memory (plus the slot sums)
+  if (es * ncomp * padded_size(ny) + 48 * 1024 > SMEM_MAX) return false;
   return true;
 }
 
@@ -560,20 +599,19 @@ int fused_make_twiddles(int len, int dtype, DevBuf &buf) {
   std::vector<double> h(2 * (size_t)len);
   const long double tau = 6.283185307179586476925286766559005768394L;
   for (int j = 0; j < len; j++) {
-    // exact octant symmetries keep the table accurate to < 1 ulp
     long double ang = -tau * (long double)j / (long double)len;
     h[2 * j] = (double)cosl(ang);
     h[2 * j + 1] = (double)sinl(ang);
   }
   if (dtype == OX_F64) {
     OX_CUDA(cudaMemcpyAsync(buf.p, h.data(), es * len, cudaMemcpyHostToDevice, g_stream));
+    OX_CUDA(cudaStreamSynchronize(g_stream));
   } else {
     std::vector<float> hf(2 * (size_t)len);
     for (size_t i = 0; i < hf.size(); i++) hf[i] = (float)h[i];
     OX_CUDA(cudaMemcpyAsync(buf.p, hf.data(), es * len, cudaMemcpyHostToDevice, g_stream));
     OX_CUDA(cudaStreamSynchronize(g_stream));
   }
-  OX_CUDA(cudaStreamSynchronize(g_stream));
   return OX_OK;
 }
 
@@ -708,8 +746,8 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
   OX_TRY(st);
   int nbins = pl->b->nslots - 2;
   dim3 grid((ns * nbins * 32 + 255) / 256, nsim);
-  bandpower_finalize2_kernel<T2><<<grid, 256, 0, g_stream>>>(pl->partial.as<double>(), nblk, ns, pl->b->nslots,
-                                                             pl->b->invcount.as<double>(), pl->p->normfact, pl->bp.as<double>());
+  bandpower_finalize2_kernel<<<grid, 256, 0, g_stream>>>(pl->partial.as<double>(), nblk, ns, pl->b->nslots,
+                                                         pl->b->invcount.as<double>(), pl->p->normfact, pl->bp.as<double>());
   OX_KERNEL_CHECK();
   OX_MARK(5);
 #undef OX_MARK
