@@ -6,10 +6,13 @@ lensed TT spectrum at 0.5 arcmin, 72 bandpowers), one process per GPU.
   python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, liborphx.so)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle) on host cores
 
-A step = one batch of --batch maps per GPU through ox_pipeline_run:
-  hand-written sim_fill (Philox noise x covsqrt, Hermitian half plane) -> cuFFT Z2D ->
-  hand-written taper multiply (the real map is materialised in HBM) -> cuFFT D2Z ->
-  hand-written fused |k|^2 + annular binning -> Statistics triple.
+A step = one batch of --batch maps per GPU through ox_pipeline_run.  On power-of-two maps the
+pipeline is three hand-written kernels (orphics_b200/csrc/ox_fused.cu):
+  K_A Philox noise x covsqrt -> inverse FFT along y        (writes the transposed half plane)
+  K_B inverse FFT along x -> real map (stored) x taper -> forward FFT along x
+  K_C forward FFT along y -> |k|^2 -> deterministic annular binning -> bandpowers
+followed by the Statistics triple; other sizes use cuFFT passes with hand-written kernels
+around them (ORPHX_PIPELINE=cufft forces that path).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -33,14 +36,18 @@ METRIC = "maps/sec sim->FFT->power2d->bin2D at 2048^2 fp64"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=128, help="timed steps (128 x 64 maps ~ 0.7 s on one B200)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="maps per step per GPU")
     ap.add_argument("--npix", type=int, default=2048)
     ap.add_argument("--res", type=float, default=0.5, help="pixel size, arcmin")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--noise", default="philox", choices=["philox", "philox_hermitian"])
+    ap.add_argument("--noise", default="philox_hermitian", choices=["philox", "philox_hermitian"],
+                    help="philox_hermitian draws the Hermitian half plane directly (N normals per map); "
+                         "philox draws the reference's full complex plane (4N normals per map)")
+    ap.add_argument("--no-keep-maps", action="store_true", help="do not store the real-space maps in HBM")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--pol", action="store_true", help="IQU sims, 6 spectra (configs[2])")
     ap.add_argument("--no-window", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=6, help="maps timed for cpu_baseline (0 = skip)")
@@ -59,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -180,6 +187,7 @@ def workload_config(args, batch, ngpu):
             f"configs[2]: IQU {args.npix}x{args.npix} ({args.res}') sims with TEB rotation, 6 binned auto/cross spectra",
             "maps_per_step_per_gpu": batch, "global_batch": batch * ngpu, "npix": args.npix, "ncomp": 3 if args.pol else 1,
             "nbins": len(EDGES) - 1, "noise": args.noise, "window": not args.no_window,
+            "maps_materialised_in_hbm": not args.no_keep_maps,
             "parallelism": f"realisations sharded over {ngpu} GPU(s) (mpi_distribute rule), one all-reduce of the Statistics triple",
             "l2": "working set per step (batch x 67 MB of maps+Fourier planes) >> 126 MB L2; no flush needed"}
 
@@ -215,7 +223,8 @@ def run_ours(args):
     window = None if args.no_window else np.asarray(maps.get_taper(shape, wcs)[0])
     pipe = maps.SimPipeline(mg, fc, binner, window=window)
     mode = _capi.NOISE_MODES[args.noise]
-    flags = pipe._flags(False, False)
+    # the real-space maps are materialised in HBM (SURVEY 8d anti-short-circuit rule) unless asked not to
+    flags = pipe._flags(False, False, keep_maps=not args.no_keep_maps)
 
     # shard: the job is ws*K*B realisations, contiguous blocks per rank (mpi.py:78-91)
     total = ws * K * B
@@ -300,14 +309,26 @@ def run_ours(args):
     s = 4 if args.dtype == "f32" else 8
     Npx = npix * npix
     nc = 3 if pol else 1
-    alg = {"sim_fill": nc * s * Npx, "cufft_inverse": nc * 4 * s * Npx, "window": nc * 2 * s * Npx if window is not None else 0,
-           "cufft_forward": nc * 4 * s * Npx, "power_bin": nc * s * Npx + Npx, "statistics": 0}
+    keep = 0 if args.no_keep_maps else 1
+    if pipe.path == "fused":
+        # three hand-written kernels; bytes = what each one must move (half planes are s*N bytes)
+        names = {"sim_fill": "K_A sim+col_ifft", "cufft_inverse": "K_B row_c2r+taper+r2c", "power_bin": "K_C col_fft+power+bin",
+                 "statistics": "statistics"}
+        alg = {"K_A sim+col_ifft": nc * s * Npx, "K_B row_c2r+taper+r2c": nc * (2 + keep) * s * Npx,
+               "K_C col_fft+power+bin": nc * s * Npx + Npx, "statistics": 0}
+        ours_keys = ["K_A sim+col_ifft", "K_B row_c2r+taper+r2c", "K_C col_fft+power+bin"]
+    else:
+        names = {k2: k2 for k2 in pipe.STAGES}
+        alg = {"sim_fill": nc * s * Npx, "cufft_inverse": nc * 4 * s * Npx, "window": nc * 2 * s * Npx if window is not None else 0,
+               "cufft_forward": nc * 4 * s * Npx, "power_bin": nc * s * Npx + Npx, "statistics": 0}
+        ours_keys = ["sim_fill", "window", "power_bin"]
     reps = 5
-    acc = {k: 0.0 for k in pipe.STAGES}
+    acc = {k: 0.0 for k in alg}
     for r in range(reps):
         st = pipe.profile(seeds_pin.array[r % K], B, mode, flags)
         for k2, v in st.items():
-            acc[k2] += v / reps
+            if k2 in names:
+                acc[names[k2]] += v / reps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -316,20 +337,49 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     stages = {}
-    for k2 in pipe.STAGES:
+    for k2 in alg:
         gbs = alg[k2] * B / (acc[k2] * 1e-3) / 1e9 if acc[k2] > 0 and alg[k2] else None
         stages[k2] = {"ms_per_launch": acc[k2], "algorithmic_bytes_per_map": alg[k2], "achieved_gbs": gbs,
                       "frac": gbs / peak if gbs else None}
-    ours = {k2: stages[k2] for k2 in ("sim_fill", "window", "power_bin")}
+    ours = {k2: stages[k2] for k2 in ours_keys}
     dom = max(ours, key=lambda k2: ours[k2]["ms_per_launch"])
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per map from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if npix == 2048 and args.dtype == "f64" and not pol and dom in tj["kernels"]:
+            traffic = tj["kernels"][dom]["dram_bytes_per_map"] * B
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dom] * B}
+                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom] * B,
+                "note": "per-kernel bytes are the fused kernel's own minimum traffic; the kernels are bound by shared-memory "
+                        "bandwidth and FP64 issue (FFT butterflies, Box-Muller), not by HBM -- see roofline_pipeline for the "
+                        "BASELINE metric's fraction"}
     pipe_bytes = (10 * s + 1) * Npx * nc if not pol else (30 * s + 1) * Npx
     pipe_gbs = value / ws * pipe_bytes / 1e9
     roofline_pipeline = {"bound": "hbm", "algorithmic_bytes_per_map": pipe_bytes, "achieved": pipe_gbs, "peak": peak,
                          "unit": "GB/s", "frac": pipe_gbs / peak,
                          "note": "(10s+1)N per T map (SURVEY 8d); the taper RMW pass (2sN) is real traffic that the formula does not credit"}
+
+    variants = None
+    if ws == 1 and not args.no_extras:
+        def timed(vmode, vflags, steps=4):
+            pipe.run_raw(warm_pin.array, B, vmode, vflags, None)
+            _capi.synchronize()
+            tm = _capi.Timer()
+            tm.start()
+            for k in range(steps):
+                pipe.run_raw(seeds_pin.array[k % K], B, vmode, vflags, None)
+            tm.stop()
+            return steps * B / (tm.elapsed_ms() / 1e3)
+        variants = {
+            "philox_fullplane_noise_maps_per_s": timed(_capi.NOISE_PHILOX, flags),
+            "philox_hermitian_noise_maps_per_s": timed(_capi.NOISE_PHILOX_HERMITIAN, flags),
+            "without_storing_maps_maps_per_s": timed(mode, flags & ~_capi.FLAG_KEEP_MAPS),
+            "note": "same pipeline, 4 steps each: the reference's full complex-plane noise (4N normals/map) vs the "
+                    "Hermitian half-plane draw (N normals/map); and without materialising the real-space maps in HBM"}
+        pipe.reset_stats()
 
     cpu = None
     if ws == 1 and args.cpu_sample > 0:
@@ -348,6 +398,7 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "roofline_pipeline": roofline_pipeline, "stages": stages, "cpu_baseline": cpu,
         "check": {"stat_N": int(N_stat), "mean_binned_over_theory_TT": ratio},
+        "variants": variants, "pipeline_path": pipe.path,
         "device": _capi.device_name(),
     }
     print(json.dumps(line))
