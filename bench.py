@@ -408,6 +408,18 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    import builtins
+    _print = builtins.print
+
+    def print_json(*a, **k):
+        _print(*a, **k, file=real_stdout)
+        real_stdout.flush()
+    builtins.print = print_json
     if args.impl == "reference":
         run_reference(args)
     else:
