@@ -179,15 +179,27 @@ int ox_pipeline_stats_reset(ox_pipeline *pl);
 
 /* ---- lensing.qest (tutorials/tt_verification.ipynb:81,608,610; lensing.py:973-976) */
 enum { OX_QE_TT = 0, OX_QE_EB = 1 };
-/* filters are full-plane [ny][nx] float64: wxy = W_XY, wy = W_Y, norm = A_L-multiplier*kmask_K */
+/* filters are full-plane [ny][nx] float64: wxy = W_XY, wy = W_Y (filter x mask x beam, the historical
+ * QuadNorm.WXY/WY), norm = the multiplier applied in kappa_from_map, N_L 2/(L(L+1)), x kmask_K.
+ * real_path != 0 (TT only): the filters vanish on the Nyquist row/column and are symmetric under
+ * l -> -l, so every field is real and the chain runs on half planes with r2c/c2r transforms. */
 int ox_qeplan_create(ox_geometry *g, int est, const double *wxy, const double *wy, const double *norm, int where, int dtype,
-                     int max_batch, ox_qeplan **out);
+                     int max_batch, int real_path, ox_qeplan **out);
 int ox_qeplan_destroy(ox_qeplan *q);
-/* kappa_from_map: inputs are real maps [nbatch][ny][nx] (X leg; Y leg may be NULL = same) or with
- * alreadyFTed full-plane complex; output real kappa map or (returnFt) full-plane complex kappa(l).
- * meanfield_accum (device, may be NULL): complex full-plane accumulator += kappa(l), count += nbatch */
+/* qest.kappa_from_map(XY, X-leg, Y-leg, alreadyFTed, returnFt) for nbatch realisations.  x = T (TT) or
+ * E (EB), y = NULL/same (TT) or B (EB); real maps [nbatch][ny][nx] of the plan dtype, or with already_ft
+ * full-plane complex k-maps.  Output: real kappa maps, or (return_ft) full-plane complex kappa_hat(l).
+ * accumulate_meanfield: add every kappa_hat(l) (half plane) and nbatch to the plan's mean-field stack. */
 int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int nbatch, int already_ft, int return_ft,
-                      void *kappa_out, int out_where);
+                      int accumulate_meanfield, void *kappa_out, int out_where);
+/* device pointers of the mean-field stack (complex128 [ny][nx/2+1] sum of kappa_hat(l)) and its int64
+ * count, for an in-place NCCL all-reduce (Statistics.add_stack / allreduce, stats.py:1134-1158,1227-1228) */
+int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem);
+int ox_qe_meanfield_reset(ox_qeplan *q);
+
+/* ---- generic batched c2c FFT on full-plane complex arrays (pixell.fft.fft / ifft, lensing.py:20):
+ * out = scale * FFT_direction(in), direction -1 forward / +1 backward, nplanes arrays [ny][nx] */
+int ox_fft_c2c(ox_powerplan *p, const void *in, int where, int nplanes, int direction, double scale, void *out, int out_where);
 
 #ifdef __cplusplus
 }

@@ -97,9 +97,12 @@ SIGNATURES = {
     "ox_pipeline_profile": [_vp, _vp, _i, _i, _i, C.POINTER(C.c_float)],
     "ox_pipeline_stats": [_vp, _pvp, _pvp, _pvp, C.POINTER(_i)],
     "ox_pipeline_stats_reset": [_vp],
-    "ox_qeplan_create": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _pvp],
+    "ox_qeplan_create": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _pvp],
     "ox_qeplan_destroy": [_vp],
-    "ox_qe_reconstruct": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i],
+    "ox_qe_reconstruct": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i],
+    "ox_qe_meanfield": [_vp, _pvp, _pvp, _pll],
+    "ox_qe_meanfield_reset": [_vp],
+    "ox_fft_c2c": [_vp, _vp, _i, _i, _i, _d, _vp, _i],
 }
 
 for _name, _args in SIGNATURES.items():

@@ -267,6 +267,24 @@ int ox_power_ifft(ox_powerplan *p, const void *kmap, int where, int nbatch, void
   return stage_out(out, out_where, p->full1.p, bytes);
 }
 
+int ox_fft_c2c(ox_powerplan *p, const void *in, int where, int nplanes, int direction, double scale, void *out, int out_where) {
+  OX_REQUIRE(p && in && out && nplanes >= 1, "ox_fft_c2c: bad arguments");
+  OX_REQUIRE(direction == 1 || direction == -1, "direction must be -1 (forward) or +1 (backward)");
+  ox_geometry *g = p->g;
+  size_t es = elem_size(p->dtype);
+  long long n = (long long)nplanes * g->ny * g->nx;
+  size_t bytes = 2 * es * (size_t)n;
+  OX_TRY(p->full1.ensure(bytes));
+  OX_CUDA(cudaMemcpyAsync(p->full1.p, in, bytes, where == OX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, g_stream));
+  OX_TRY(p->fft.exec_c2c(nplanes, p->full1.p, p->full1.p, direction > 0 ? CUFFT_INVERSE : CUFFT_FORWARD));
+  if (scale != 1.0) {
+    if (p->dtype == OX_F64) scale_complex_kernel<double2><<<grid_1d(n, 256), 256, 0, g_stream>>>(p->full1.as<double2>(), n, scale);
+    else scale_complex_kernel<float2><<<grid_1d(n, 256), 256, 0, g_stream>>>(p->full1.as<float2>(), n, scale);
+    OX_KERNEL_CHECK();
+  }
+  return stage_out(out, out_where, p->full1.p, bytes);
+}
+
 int ox_power_f2power(ox_powerplan *p, const void *k1, const void *k2, int where, long long n, int flags, void *out, int out_where) {
   OX_REQUIRE(p && k1 && k2 && out && n > 0, "ox_power_f2power: bad arguments");
   size_t es = elem_size(p->dtype);

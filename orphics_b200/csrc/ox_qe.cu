@@ -1,14 +1,434 @@
-// lensing.qest on the device -- placeholder until the estimator kernels land.
+// lensing.qest.kappa_from_map on the device (call sites tutorials/tt_verification.ipynb:608,610;
+// lensing.py:973-976; arithmetic restated in oracle/qe_np.py from the historical estimator):
+//
+//   kappa_hat(l) = -A_L(l) M_K(l) FFT[ Re IFFT( i lx P_x + i ly P_y ) ],
+//   P_{x,y} = FFT[ IFFT(i l_{x,y} k_X W_XY phase) . conj IFFT(k_Y W_Y phase phaseB) ]
+//
+// TT with filters that vanish on the Nyquist row/column (any lmax below Nyquist) involves only
+// Hermitian Fourier arrays and real fields: it runs on half planes with cuFFT Z2D/D2Z -- half the
+// bytes of the reference's c2c transforms -- and the reference's ifft -> .real -> fft round trip is
+// the identity.  EB (spin-2 phases -> complex real-space fields) and TT with unsymmetric filters
+// run the general full-plane c2c chain; the round trip becomes a Hermitian projection
+// 1/2 [F(p) + conj F(p')] in the final kernel.  Elementwise work is fused into three kernels:
+// legs (1 read, 3 writes), real-space products (3 reads, 2 writes), divergence x normalisation
+// (2 reads, 1 write, + the mean-field accumulator).
+#include <math.h>
+
 #include "ox_common.cuh"
+
 using namespace ox;
+
+struct ox_qeplan {
+  ox_geometry *g = nullptr;
+  int est = OX_QE_TT, dtype = OX_F64, max_batch = 1;
+  bool real_path = false;  // TT on half planes
+  FFTPlans fft;
+  DevBuf wxy, wy, norm;    // T [ny][nx] full plane (general) or [ny][nxh] (real path)
+  DevBuf kx, ky;           // staged inputs (half or full plane complex)
+  DevBuf in_real;          // staged real maps
+  DevBuf legs, fields, prod, pk, khat, full, out_real;
+  DevBuf mf;               // double2 [ny][nxh] mean-field accumulator of kappa_hat(l)
+  DevBuf mf_count;         // int64
+};
+
+namespace {
+
+constexpr int QT = 256;
+
+template <typename T2>
+__device__ __forceinline__ T2 mk(double x, double y) {
+  T2 r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+
+// e^{2 i theta}, theta = atan2(ly, lx); 1 at l = 0
+__device__ __forceinline__ void phase2(double y, double x, double &c, double &s) {
+  double l2 = y * y + x * x;
+  c = 1.0;
+  s = 0.0;
+  if (l2 > 0.0) {
+    double inv = 1.0 / l2;
+    c = (x * x - y * y) * inv;
+    s = 2.0 * x * y * inv;
+  }
+}
+
+// ---- TT on half planes -------------------------------------------------------------------
+// legs[m][0] = i lx k W_XY / N, legs[m][1] = i ly k W_XY / N, legs[m][2] = k W_Y / N
+template <typename T, typename T2>
+__global__ void qe_tt_legs_kernel(const T2 *__restrict__ kx, const T2 *__restrict__ ky, const T *__restrict__ wxy,
+                                  const T *__restrict__ wy, const double *__restrict__ ly, const double *__restrict__ lx,
+                                  int ny, int nxh, double invn, T2 *__restrict__ legs) {
+  const long long nh = (long long)ny * nxh;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const long long m = blockIdx.y;
+  const int iy = (int)(i / nxh), ix = (int)(i - (long long)iy * nxh);
+  T2 a = kx[m * nh + i], b = ky[m * nh + i];
+  double wg = (double)wxy[i] * invn, wh = (double)wy[i] * invn;
+  double gx = lx[ix] * wg, gy = ly[iy] * wg;
+  T2 *o = legs + m * 3 * nh + i;
+  o[0] = mk<T2>(-(double)a.y * gx, (double)a.x * gx);  // i * a * gx
+  o[nh] = mk<T2>(-(double)a.y * gy, (double)a.x * gy);
+  o[2 * nh] = mk<T2>((double)b.x * wh, (double)b.y * wh);
+}
+
+// prod[m][0] = gx*h, prod[m][1] = gy*h  (real fields [m][3][n])
+template <typename T>
+__global__ void qe_tt_prod_kernel(const T *__restrict__ f, long long n, T *__restrict__ prod) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long m = blockIdx.y;
+  const T *p = f + m * 3 * n + i;
+  T h = p[2 * n];
+  prod[m * 2 * n + i] = p[0] * h;
+  prod[(m * 2 + 1) * n + i] = p[n] * h;
+}
+
+// khat[m] = -norm (i lx Px + i ly Py)   (half plane); optional mean-field accumulation over m
+template <typename T, typename T2>
+__global__ void qe_tt_div_kernel(const T2 *__restrict__ pk, const T *__restrict__ norm, const double *__restrict__ ly,
+                                 const double *__restrict__ lx, int ny, int nx, int nxh, int nb, T2 *__restrict__ khat,
+                                 double2 *__restrict__ mf) {
+  const long long nh = (long long)ny * nxh;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const int iy = (int)(i / nxh), ix = (int)(i - (long long)iy * nxh);
+  // on the Nyquist column/row the reference's ifft -> .real -> fft projects the odd l_x / l_y term away
+  const double x = (2 * ix == nx) ? 0.0 : lx[ix], y = (2 * iy == ny) ? 0.0 : ly[iy], a = -(double)norm[i];
+  double2 acc = mf ? mf[i] : make_double2(0.0, 0.0);
+  for (int m = 0; m < nb; m++) {
+    T2 px = pk[(long long)m * 2 * nh + i], py = pk[((long long)m * 2 + 1) * nh + i];
+    double fr = -(x * (double)px.y + y * (double)py.y), fi = x * (double)px.x + y * (double)py.x;  // i (x px + y py)
+    double kr = a * fr, ki = a * fi;
+    khat[(long long)m * nh + i] = mk<T2>(kr, ki);
+    acc.x += kr;
+    acc.y += ki;
+  }
+  if (mf) mf[i] = acc;
+}
+
+// ---- general full-plane chain (EB, or TT with unsymmetric filters) ---------------------------
+template <typename T, typename T2, bool SPIN2>
+__global__ void qe_gen_legs_kernel(const T2 *__restrict__ kx, const T2 *__restrict__ ky, const T *__restrict__ wxy,
+                                   const T *__restrict__ wy, const double *__restrict__ ly, const double *__restrict__ lx,
+                                   int ny, int nx, double invn, T2 *__restrict__ legs) {
+  const long long n = (long long)ny * nx;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long m = blockIdx.y;
+  const int iy = (int)(i / nx), ix = (int)(i - (long long)iy * nx);
+  const double x = lx[ix], y = ly[iy];
+  T2 a = kx[m * n + i], b = ky[m * n + i];
+  double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+  if (SPIN2) {
+    double c, s;
+    phase2(y, x, c, s);
+    double tr = ar * c - ai * s, ti = ar * s + ai * c;  // k_E e^{2 i theta}
+    ar = tr; ai = ti;
+    tr = br * c - bi * s; ti = br * s + bi * c;          // k_B e^{2 i theta}
+    br = -ti; bi = tr;                                   // x phaseB = i
+  }
+  double wg = (double)wxy[i] * invn, wh = (double)wy[i] * invn;
+  T2 *o = legs + m * 3 * n + i;
+  o[0] = mk<T2>(-ai * x * wg, ar * x * wg);
+  o[n] = mk<T2>(-ai * y * wg, ar * y * wg);
+  o[2 * n] = mk<T2>(br * wh, bi * wh);
+}
+
+// prod[m][0] = gx conj(h), prod[m][1] = gy conj(h)
+template <typename T2>
+__global__ void qe_gen_prod_kernel(const T2 *__restrict__ f, long long n, T2 *__restrict__ prod) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long m = blockIdx.y;
+  const T2 *p = f + m * 3 * n + i;
+  T2 gx = p[0], gy = p[n], h = p[2 * n];
+  prod[m * 2 * n + i] = mk<T2>((double)gx.x * h.x + (double)gx.y * h.y, (double)gx.y * h.x - (double)gx.x * h.y);
+  prod[(m * 2 + 1) * n + i] = mk<T2>((double)gy.x * h.x + (double)gy.y * h.y, (double)gy.y * h.x - (double)gy.x * h.y);
+}
+
+// F = i lx Px + i ly Py; the reference's ifft -> .real -> fft is the Hermitian projection
+// Fp(p) = 1/2 [F(p) + conj F(p')].  Outputs for half-plane pixels p (p' = mirrored pixel):
+//   full[m](p) = -norm(p) Fp(p), full[m](p') = -norm(p') conj Fp(p)      (returnFt, what the reference returns)
+//   khat[m](p) = -1/2 (norm(p) + norm(p')) Fp(p)   = Hermitian part of the above (kappa map, mean field)
+template <typename T, typename T2>
+__global__ void qe_gen_div_kernel(const T2 *__restrict__ pk, const T *__restrict__ norm, const double *__restrict__ ly,
+                                  const double *__restrict__ lx, int ny, int nx, int nxh, int nb, T2 *__restrict__ khat,
+                                  T2 *__restrict__ full, double2 *__restrict__ mf) {
+  const long long nh = (long long)ny * nxh, n = (long long)ny * nx;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const int iy = (int)(i / nxh), ix = (int)(i - (long long)iy * nxh);
+  const int my = iy ? ny - iy : 0, mx = ix ? nx - ix : 0;
+  const long long p = (long long)iy * nx + ix, q = (long long)my * nx + mx;
+  const double x = lx[ix], y = ly[iy], xq = lx[mx], yq = ly[my];
+  const double np_ = (double)norm[p], nq = (double)norm[q], a = -0.5 * (np_ + nq);
+  double2 acc = mf ? mf[i] : make_double2(0.0, 0.0);
+  for (int m = 0; m < nb; m++) {
+    const T2 *base = pk + (long long)m * 2 * n;
+    T2 px = base[p], py = base[n + p], qx = base[q], qy = base[n + q];
+    double fr = -(x * (double)px.y + y * (double)py.y), fi = x * (double)px.x + y * (double)py.x;
+    double gr = -(xq * (double)qx.y + yq * (double)qy.y), gi = xq * (double)qx.x + yq * (double)qy.x;
+    double pr = 0.5 * (fr + gr), pi = 0.5 * (fi - gi);  // Fp(p)
+    double kr = a * pr, ki = a * pi;
+    khat[(long long)m * nh + i] = mk<T2>(kr, ki);
+    if (full) {
+      full[(long long)m * n + p] = mk<T2>(-np_ * pr, -np_ * pi);
+      full[(long long)m * n + q] = mk<T2>(-nq * pr, nq * pi);
+    }
+    acc.x += kr;
+    acc.y += ki;
+  }
+  if (mf) mf[i] = acc;
+}
+
+// ---- layout helpers ---------------------------------------------------------------------------
+template <typename T2>
+__global__ void full_to_half_kernel(const T2 *__restrict__ full, int ny, int nx, int nxh, T2 *__restrict__ half) {
+  const long long nh = (long long)ny * nxh;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const long long m = blockIdx.y;
+  const int iy = (int)(i / nxh), ix = (int)(i - (long long)iy * nxh);
+  half[m * nh + i] = full[m * (long long)ny * nx + (long long)iy * nx + ix];
+}
+
+template <typename T2>
+__global__ void half_to_full_kernel(const T2 *__restrict__ half, int ny, int nx, int nxh, double scale, T2 *__restrict__ full) {
+  const long long n = (long long)ny * nx, nh = (long long)ny * nxh;
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const long long m = blockIdx.y;
+  const int iy = (int)(p / nx), ix = (int)(p - (long long)iy * nx);
+  const bool mirror = ix >= nxh;
+  const int sy = mirror ? (iy ? ny - iy : 0) : iy, sx = mirror ? nx - ix : ix;
+  T2 z = half[m * nh + (long long)sy * nxh + sx];
+  full[m * n + p] = mk<T2>((double)z.x * scale, (mirror ? -(double)z.y : (double)z.y) * scale);
+}
+
+template <typename T2>
+__global__ void scale_half_kernel(T2 *__restrict__ a, long long n, double s) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    T2 z = a[i];
+    a[i] = mk<T2>((double)z.x * s, (double)z.y * s);
+  }
+}
+
+// take the half-plane columns of a full-plane real table
+template <typename T>
+__global__ void table_half_kernel(const T *__restrict__ full, int ny, int nx, int nxh, T *__restrict__ half) {
+  const long long nh = (long long)ny * nxh;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const int iy = (int)(i / nxh), ix = (int)(i - (long long)iy * nxh);
+  half[i] = full[(long long)iy * nx + ix];
+}
+
+template <typename T, typename T2>
+int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb, int already_ft, int return_ft,
+                  int accumulate, void *out, int out_where) {
+  ox_geometry *g = q->g;
+  const int ny = g->ny, nx = g->nx, nxh = g->nxh;
+  const long long n = (long long)ny * nx, nh = (long long)ny * nxh;
+  const double invn = 1.0 / ((double)ny * (double)nx);
+  const double *ly = g->ly.as<double>(), *lx = g->lx.as<double>();
+  const bool two = (y != nullptr && y != x);
+  const long long plane = q->real_path ? nh : n;  // complex elements per staged k-map
+  OX_TRY(q->kx.ensure(sizeof(T2) * (size_t)q->max_batch * plane));
+  if (two) OX_TRY(q->ky.ensure(sizeof(T2) * (size_t)q->max_batch * plane));
+  // ---- inputs -> k-maps in the layout of the chosen path
+  for (int leg = 0; leg < (two ? 2 : 1); leg++) {
+    const void *src = leg ? y : x;
+    T2 *dstk = leg ? q->ky.as<T2>() : q->kx.as<T2>();
+    if (already_ft) {
+      const void *dsrc;
+      OX_TRY(stage_in(src, where, sizeof(T2) * (size_t)nb * n, q->full, &dsrc));
+      if (q->real_path) {
+        dim3 grid((unsigned)((nh + QT - 1) / QT), nb);
+        full_to_half_kernel<T2><<<grid, QT, 0, g_stream>>>((const T2 *)dsrc, ny, nx, nxh, dstk);
+        OX_KERNEL_CHECK();
+      } else {
+        OX_CUDA(cudaMemcpyAsync(dstk, dsrc, sizeof(T2) * (size_t)nb * n, cudaMemcpyDeviceToDevice, g_stream));
+      }
+    } else {
+      OX_TRY(q->in_real.ensure(sizeof(T) * (size_t)q->max_batch * n));
+      OX_CUDA(cudaMemcpyAsync(q->in_real.p, src, sizeof(T) * (size_t)nb * n,
+                              where == OX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, g_stream));
+      if (q->real_path) {
+        OX_TRY(q->fft.exec_r2c(nb, q->in_real.p, dstk));
+      } else {
+        OX_TRY(q->khat.ensure(sizeof(T2) * (size_t)q->max_batch * nh));
+        OX_TRY(q->fft.exec_r2c(nb, q->in_real.p, q->khat.p));
+        dim3 grid((unsigned)((n + QT - 1) / QT), nb);
+        half_to_full_kernel<T2><<<grid, QT, 0, g_stream>>>(q->khat.as<T2>(), ny, nx, nxh, 1.0, dstk);
+        OX_KERNEL_CHECK();
+      }
+    }
+  }
+  const T2 *kx = q->kx.as<T2>(), *ky = two ? q->ky.as<T2>() : kx;
+  OX_TRY(q->khat.ensure(sizeof(T2) * (size_t)q->max_batch * nh));
+  double2 *mf = accumulate ? q->mf.as<double2>() : nullptr;
+  if (q->real_path) {
+    OX_TRY(q->legs.ensure(sizeof(T2) * (size_t)q->max_batch * 3 * nh));
+    OX_TRY(q->fields.ensure(sizeof(T) * (size_t)q->max_batch * 3 * n));
+    OX_TRY(q->prod.ensure(sizeof(T) * (size_t)q->max_batch * 2 * n));
+    OX_TRY(q->pk.ensure(sizeof(T2) * (size_t)q->max_batch * 2 * nh));
+    dim3 gh((unsigned)((nh + QT - 1) / QT), nb), gf((unsigned)((n + QT - 1) / QT), nb);
+    qe_tt_legs_kernel<T, T2><<<gh, QT, 0, g_stream>>>(kx, ky, q->wxy.as<T>(), q->wy.as<T>(), ly, lx, ny, nxh, invn, q->legs.as<T2>());
+    OX_KERNEL_CHECK();
+    OX_TRY(q->fft.exec_c2r(3 * nb, q->legs.p, q->fields.p));
+    qe_tt_prod_kernel<T><<<gf, QT, 0, g_stream>>>(q->fields.as<T>(), n, q->prod.as<T>());
+    OX_KERNEL_CHECK();
+    OX_TRY(q->fft.exec_r2c(2 * nb, q->prod.p, q->pk.p));
+    qe_tt_div_kernel<T, T2><<<(unsigned)((nh + QT - 1) / QT), QT, 0, g_stream>>>(q->pk.as<T2>(), q->norm.as<T>(), ly, lx, ny, nx, nxh, nb,
+                                                                              q->khat.as<T2>(), mf);
+    OX_KERNEL_CHECK();
+  } else {
+    OX_TRY(q->legs.ensure(sizeof(T2) * (size_t)q->max_batch * 3 * n));
+    OX_TRY(q->pk.ensure(sizeof(T2) * (size_t)q->max_batch * 2 * n));
+    dim3 gf((unsigned)((n + QT - 1) / QT), nb);
+    if (q->est == OX_QE_EB)
+      qe_gen_legs_kernel<T, T2, true><<<gf, QT, 0, g_stream>>>(kx, ky, q->wxy.as<T>(), q->wy.as<T>(), ly, lx, ny, nx, invn, q->legs.as<T2>());
+    else
+      qe_gen_legs_kernel<T, T2, false><<<gf, QT, 0, g_stream>>>(kx, ky, q->wxy.as<T>(), q->wy.as<T>(), ly, lx, ny, nx, invn, q->legs.as<T2>());
+    OX_KERNEL_CHECK();
+    OX_TRY(q->fft.exec_c2c(3 * nb, q->legs.p, q->legs.p, CUFFT_INVERSE));
+    qe_gen_prod_kernel<T2><<<gf, QT, 0, g_stream>>>(q->legs.as<T2>(), n, q->pk.as<T2>());
+    OX_KERNEL_CHECK();
+    OX_TRY(q->fft.exec_c2c(2 * nb, q->pk.p, q->pk.p, CUFFT_FORWARD));
+    T2 *fullp = nullptr;
+    if (return_ft) {
+      fullp = (T2 *)out;
+      if (out_where == OX_HOST) {
+        OX_TRY(q->full.ensure(sizeof(T2) * (size_t)nb * n));
+        fullp = q->full.as<T2>();
+      }
+    }
+    qe_gen_div_kernel<T, T2><<<(unsigned)((nh + QT - 1) / QT), QT, 0, g_stream>>>(q->pk.as<T2>(), q->norm.as<T>(), ly, lx, ny, nx, nxh,
+                                                                               nb, q->khat.as<T2>(), fullp, mf);
+    OX_KERNEL_CHECK();
+    if (return_ft) {
+      if (out_where == OX_HOST) OX_TRY(stage_out(out, OX_HOST, fullp, sizeof(T2) * (size_t)nb * n));
+      return OX_OK;
+    }
+  }
+  // ---- outputs
+  if (return_ft) {
+    size_t bytes = sizeof(T2) * (size_t)nb * n;
+    void *dst = out;
+    if (out_where == OX_HOST) {
+      OX_TRY(q->full.ensure(bytes));
+      dst = q->full.p;
+    }
+    dim3 gf((unsigned)((n + QT - 1) / QT), nb);
+    half_to_full_kernel<T2><<<gf, QT, 0, g_stream>>>(q->khat.as<T2>(), ny, nx, nxh, 1.0, (T2 *)dst);
+    OX_KERNEL_CHECK();
+    if (out_where == OX_HOST) OX_TRY(stage_out(out, OX_HOST, dst, bytes));
+    return OX_OK;
+  }
+  // real-space kappa = IFFT(kappa_hat)/N: scale a copy so the mean field keeps the unscaled values
+  size_t bytes = sizeof(T) * (size_t)nb * n;
+  OX_TRY(q->out_real.ensure(sizeof(T) * (size_t)q->max_batch * n));
+  scale_half_kernel<T2><<<sm_count() * 8, QT, 0, g_stream>>>(q->khat.as<T2>(), (long long)nb * nh, invn);
+  OX_KERNEL_CHECK();
+  OX_TRY(q->fft.exec_c2r(nb, q->khat.p, q->out_real.p));
+  return stage_out(out, out_where, q->out_real.p, bytes);
+}
+
+__global__ void add_count_kernel(long long *c, long long v) { *c += v; }
+
+template <typename T>
+int upload_tables(ox_qeplan *q, const double *wxy, const double *wy, const double *norm, int where) {
+  ox_geometry *g = q->g;
+  const long long n = (long long)g->ny * g->nx, nh = (long long)g->ny * g->nxh;
+  const double *src[3] = {wxy, wy, norm};
+  DevBuf *dst[3] = {&q->wxy, &q->wy, &q->norm};
+  DevBuf stage, fullT;
+  for (int t = 0; t < 3; t++) {
+    const void *d;
+    OX_TRY(stage_in(src[t], where, sizeof(double) * n, stage, &d));
+    OX_TRY(fullT.ensure(sizeof(T) * n));
+    OX_TRY(cast_from_f64((const double *)d, fullT.p, n, q->dtype));
+    if (q->real_path) {
+      OX_TRY(dst[t]->ensure(sizeof(T) * nh));
+      table_half_kernel<T><<<(unsigned)((nh + QT - 1) / QT), QT, 0, g_stream>>>(fullT.as<T>(), g->ny, g->nx, g->nxh, dst[t]->as<T>());
+      OX_KERNEL_CHECK();
+    } else {
+      OX_TRY(dst[t]->ensure(sizeof(T) * n));
+      OX_CUDA(cudaMemcpyAsync(dst[t]->p, fullT.p, sizeof(T) * n, cudaMemcpyDeviceToDevice, g_stream));
+    }
+    OX_CUDA(cudaStreamSynchronize(g_stream));
+  }
+  return OX_OK;
+}
+
+}  // namespace
+
 extern "C" {
-int ox_qeplan_create(ox_geometry *, int, const double *, const double *, const double *, int, int, int, ox_qeplan **) {
-  set_error("ox_qeplan_create: not implemented yet");
-  return OX_ERR_UNSUPPORTED;
+
+int ox_qeplan_create(ox_geometry *g, int est, const double *wxy, const double *wy, const double *norm, int where, int dtype,
+                     int max_batch, int real_path, ox_qeplan **out) {
+  OX_REQUIRE(g && wxy && wy && norm && out, "ox_qeplan_create: null pointer");
+  OX_REQUIRE(est == OX_QE_TT || est == OX_QE_EB, "unknown estimator %d", est);
+  OX_REQUIRE(dtype == OX_F64 || dtype == OX_F32, "bad dtype %d", dtype);
+  OX_REQUIRE(max_batch >= 1, "max_batch must be >= 1");
+  OX_REQUIRE(!(real_path && est != OX_QE_TT), "the half-plane path is for TT only");
+  ox_qeplan *q = new ox_qeplan;
+  q->g = g;
+  q->est = est;
+  q->dtype = dtype;
+  q->max_batch = max_batch;
+  q->real_path = real_path != 0;
+  q->fft.ny = g->ny;
+  q->fft.nx = g->nx;
+  q->fft.dtype = dtype;
+  int st = dtype == OX_F64 ? upload_tables<double>(q, wxy, wy, norm, where) : upload_tables<float>(q, wxy, wy, norm, where);
+  if (st == OX_OK) st = q->mf.ensure(sizeof(double2) * (size_t)g->ny * g->nxh);
+  if (st == OX_OK) st = q->mf_count.ensure(sizeof(long long));
+  if (st != OX_OK) {
+    delete q;
+    return st;
+  }
+  *out = q;
+  return ox_qe_meanfield_reset(q);
 }
-int ox_qeplan_destroy(ox_qeplan *) { return OX_OK; }
-int ox_qe_reconstruct(ox_qeplan *, const void *, const void *, int, int, int, int, void *, int) {
-  set_error("ox_qe_reconstruct: not implemented yet");
-  return OX_ERR_UNSUPPORTED;
+
+int ox_qeplan_destroy(ox_qeplan *q) {
+  delete q;
+  return OX_OK;
 }
+
+int ox_qe_meanfield_reset(ox_qeplan *q) {
+  OX_REQUIRE(q, "null plan");
+  OX_CUDA(cudaMemsetAsync(q->mf.p, 0, sizeof(double2) * (size_t)q->g->ny * q->g->nxh, g_stream));
+  OX_CUDA(cudaMemsetAsync(q->mf_count.p, 0, sizeof(long long), g_stream));
+  return OX_OK;
 }
+
+int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem) {
+  OX_REQUIRE(q, "null plan");
+  if (accum_dev) *accum_dev = q->mf.p;
+  if (count_dev) *count_dev = q->mf_count.as<long long>();
+  if (nelem) *nelem = (long long)q->g->ny * q->g->nxh;
+  return OX_OK;
+}
+
+int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int nbatch, int already_ft, int return_ft,
+                      int accumulate_meanfield, void *kappa_out, int out_where) {
+  OX_REQUIRE(q && x && kappa_out, "ox_qe_reconstruct: null pointer");
+  OX_REQUIRE(nbatch >= 1 && nbatch <= q->max_batch, "nbatch=%d outside 1..max_batch=%d", nbatch, q->max_batch);
+  OX_REQUIRE(q->est != OX_QE_EB || (y && y != x), "EB needs the B leg");
+  int st = q->dtype == OX_F64
+               ? reconstruct_T<double, double2>(q, x, y, where, nbatch, already_ft, return_ft, accumulate_meanfield, kappa_out, out_where)
+               : reconstruct_T<float, float2>(q, x, y, where, nbatch, already_ft, return_ft, accumulate_meanfield, kappa_out, out_where);
+  if (st == OX_OK && accumulate_meanfield) {
+    add_count_kernel<<<1, 1, 0, g_stream>>>(q->mf_count.as<long long>(), (long long)nbatch);
+    OX_KERNEL_CHECK();
+  }
+  return st;
+}
+
+}  // extern "C"

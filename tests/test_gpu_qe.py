@@ -1,0 +1,141 @@
+"""GPU parity: lensing.qest through the C-ABI vs the numpy oracle on identical inputs (kappa maps and
+kappa_hat(l) <= 1e-10 relative in fp64, 1e-5 in fp32), TT on the half-plane path and on the general
+c2c path, EB, alreadyFTed / returnFt / separate Y leg / batches / mean-field stack."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import enmap_np as oenmap, maps_np as omaps, qe_np
+
+pytestmark = pytest.mark.gpu
+TOL64, TOL32 = 1e-10, 1e-5
+
+
+def setup(npix, res, theory, masked=True):
+    from orphics_b200 import maps, lensing, cosmology
+    w = npix * res
+    shape, wcs = maps.rect_geometry(width_arcmin=w, px_res_arcmin=res)
+    so, wo = omaps.rect_geometry(width_arcmin=w, px_res_arcmin=res)
+    modl = np.asarray(oenmap.modlmap(so, wo))
+    beam = omaps.gauss_beam(modl, 1.5)
+    n2d = np.zeros(so) + (1.0 * np.pi / 180 / 60) ** 2
+    if masked:
+        tm = np.asarray(omaps.mask_kspace(so, wo, lmin=300, lmax=2000))
+        km = np.asarray(omaps.mask_kspace(so, wo, lmin=20, lmax=3500))
+    else:
+        tm = km = None
+    kw = dict(noise2d=n2d, beam2d=beam, kmask=tm, noise2d_P=2 * n2d, kmask_P=tm, kmask_K=km, pol=True, grad_cut=None,
+              unlensed_equals_lensed=True, bigell=9000)               # tutorials/tt_verification.ipynb:81
+    qo = qe_np.qest(so, wo, theory, **kw)
+    q = lensing.qest(shape, wcs, cosmology.default_theory(), max_batch=3, **kw)
+    return shape, wcs, so, wo, q, qo
+
+
+@pytest.mark.parametrize("masked", [True, False])
+def test_filters_and_normalisation_match_oracle(masked, theory):
+    shape, wcs, so, wo, q, qo = setup(128, 2.0, theory, masked)
+    for XY in ("TT", "EB"):
+        assert relerr(q.N.WXY(XY), qo.N.WXY(XY)) < 1e-14
+        assert relerr(q.N.Nlkk[XY], qo.N.Nlkk[XY]) < 1e-9
+        assert relerr(q.N.AL[XY], qo.N.AL[XY]) < 1e-9
+    assert q._plans["TT"][1] == masked        # half-plane path only when the filters vanish at Nyquist
+
+
+@pytest.mark.parametrize("masked", [True, False])
+def test_tt_kappa_matches_oracle(masked, theory):
+    shape, wcs, so, wo, q, qo = setup(128, 2.0, theory, masked)
+    qo.N.AL["TT"] = np.asarray(q.N.AL["TT"])          # identical set-up input: compare the per-map chain only
+    rng = np.random.RandomState(3)
+    T = rng.standard_normal(shape) * 50
+    T2 = rng.standard_normal(shape) * 50
+    k, ko = q.kappa_from_map("TT", T), qo.kappa_from_map("TT", T)
+    assert k.shape == shape and k.dtype == np.float64
+    assert relerr(k, ko) < TOL64
+    kT = np.fft.fft2(T)
+    assert relerr(q.kappa_from_map("TT", kT, alreadyFTed=True), ko) < TOL64
+    kf, kfo = q.kappa_from_map("TT", T, returnFt=True), qo.kappa_from_map("TT", T, returnFt=True)
+    assert kf.dtype == np.complex128 and relerr(kf, kfo) < TOL64
+    assert relerr(q.reconstruct("TT", T, T2DDataY=T2), qo.kappa_from_map("TT", T, T2DDataY=T2)) < TOL64   # separate Y leg
+    # batch + mean-field stack (Statistics.add_stack semantics)
+    stack = np.stack([T, T2, T + T2])
+    q.reset_meanfield("TT")
+    kb = q.kappa_from_maps("TT", stack, returnFt=True, accumulate_meanfield=True)
+    want = np.stack([qo.kappa_from_map("TT", m, returnFt=True) for m in stack])
+    assert relerr(kb, want) < TOL64
+    acc, cnt = q.meanfield("TT")
+    assert cnt == 3
+    tot = want.sum(0)                                 # the stack keeps the Hermitian part (= what the kappa MAP sees)
+    iy, ix = (-np.arange(shape[0])) % shape[0], (-np.arange(shape[1])) % shape[1]
+    herm = 0.5 * (tot + np.conj(tot[iy][:, ix]))
+    assert relerr(acc, herm[:, :shape[1] // 2 + 1]) < TOL64
+    kb2 = q.kappa_from_maps("TT", stack, accumulate_meanfield=True)
+    assert q.meanfield("TT")[1] == 6
+    assert relerr(kb2, np.stack([qo.kappa_from_map("TT", m) for m in stack])) < TOL64
+
+
+def test_eb_kappa_matches_oracle(theory):
+    from orphics_b200 import maps
+    shape, wcs, so, wo, q, qo = setup(128, 2.0, theory, True)
+    qo.N.AL["EB"] = np.asarray(q.N.AL["EB"])
+    rng = np.random.RandomState(4)
+    iqu = rng.standard_normal((3,) + shape) * np.array([50., 3., 3.])[:, None, None]
+    fc = maps.FourierCalc((3,) + shape, wcs)
+    _, kteb, _ = fc.power2d(iqu)                                   # tutorials/tt_verification.ipynb:606
+    ofc = omaps.FourierCalc((3,) + so, wo)
+    _, ktebo, _ = ofc.power2d(oenmap.ndmap(iqu, wo))
+    assert relerr(kteb, ktebo) < TOL64
+    k = q.kappa_from_map("EB", kteb[0], kteb[1], kteb[2], alreadyFTed=True)      # ipynb:610
+    ko = qo.kappa_from_map("EB", np.asarray(ktebo[0]), np.asarray(ktebo[1]), np.asarray(ktebo[2]), alreadyFTed=True)
+    assert relerr(k, ko) < TOL64
+    kf = q.kappa_from_map("EB", kteb[0], kteb[1], kteb[2], alreadyFTed=True, returnFt=True)
+    assert relerr(kf, qo.kappa_from_map("EB", ktebo[0], ktebo[1], ktebo[2], alreadyFTed=True, returnFt=True)) < TOL64
+    E, B = rng.standard_normal((2,) + shape)
+    assert relerr(q.kappa_from_map("EB", None, E, B), qo.kappa_from_map("EB", None, E, B)) < TOL64     # real E/B maps in
+
+
+def test_fp32_mode(theory):
+    from orphics_b200 import lensing, cosmology
+    shape, wcs, so, wo, q, qo = setup(128, 2.0, theory, True)
+    q32 = lensing.qest(shape, wcs, cosmology.default_theory(), noise2d=qo.N.noise["TT"], beam2d=qo.N.beam,
+                       kmask=qo.N.fmask["TT"], kmask_K=qo.N.fmaskK, unlensed_equals_lensed=True, dtype=np.float32)
+    rng = np.random.RandomState(5)
+    T = (rng.standard_normal(shape) * 50).astype(np.float32)
+    k = q32.kappa_from_map("TT", T)
+    assert k.dtype == np.float32
+    assert relerr(k, qo.kappa_from_map("TT", T.astype(np.float64))) < 20 * TOL32   # quadratic in fp32 data
+
+
+def test_qe_recovers_input_kappa_statistically(theory):
+    """tutorials/tt_verification.ipynb:597-617 on the device: unit response to first-order lensing."""
+    from orphics_b200 import maps, lensing, stats
+    from test_oracle_qe import FirstOrderTheory, lensed_first_order
+    npix, res = 256, 1.5
+    shape, wcs = maps.rect_geometry(width_arcmin=npix * res, px_res_arcmin=res)
+    fc = maps.FourierCalc(shape, wcs, max_batch=16)
+    g = fc.geometry
+    modl = g.modlmap()
+    LY, LX = np.meshgrid(g.ly, g.lx, indexing="ij")
+    ells = np.arange(0, modl.max() + 1, 1.)
+    nlev = (1.0 * np.pi / 180 / 60) ** 2
+    mk = lambda ps: maps.MapGen(shape, wcs, ps[None, None], noise="philox", max_batch=16)
+    mgT, mgK, mgN = mk(theory.uCl("TT", ells)), mk(theory.gCl("kk", ells)), mk(np.zeros(ells.size) + nlev)
+    beam = maps.gauss_beam(modl, 1.5)
+    tmask = maps.mask_kspace(shape, wcs, lmin=300, lmax=3000)
+    kmask = maps.mask_kspace(shape, wcs, lmin=100, lmax=3000)
+    q = lensing.qest(shape, wcs, FirstOrderTheory(theory), noise2d=np.zeros(shape) + nlev, beam2d=beam, kmask=tmask,
+                     kmask_K=kmask, max_batch=16)
+    b = stats.bin2D(modl, np.linspace(100, 3000, 8), geometry=g)
+    nsim = 48
+    rs = []
+    for s0 in range(0, nsim, 16):
+        seeds = list(range(s0, s0 + 16))
+        Ts, Ks, Ns = mgT.get_maps(seeds), mgK.get_maps([s + 5000 for s in seeds]), mgN.get_maps([s + 9000 for s in seeds])
+        obs = np.stack([np.fft.ifft2(np.fft.fft2(lensed_first_order(np.asarray(T), np.asarray(K), modl, LY, LX)) * beam).real + np.asarray(N)
+                        for T, K, N in zip(Ts, Ks, Ns)])
+        rec = q.kappa_from_maps("TT", obs)
+        pc = fc.binned_power_batch(b, rec, np.asarray(Ks))[:, 0]
+        pi = fc.binned_power_batch(b, np.asarray(Ks))[:, 0]
+        rs.append(pc / pi)
+    rs = np.concatenate(rs)
+    mean, err = rs.mean(0), rs.std(0) / np.sqrt(nsim)
+    assert np.all(np.abs(mean - 1) < 4 * err + 0.03), (mean, err)
