@@ -197,6 +197,11 @@ int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int
 int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem);
 int ox_qe_meanfield_reset(ox_qeplan *q);
 
+/* maps.filter_map (maps.py:1922-1923): Re(ifft(fft(m) * kfilter)) / Npix for nbatch x ncomp real maps;
+ * kfilter is a real float64 full-plane [ny][nx] array (beam, l-mask, Wiener filter) */
+int ox_power_filter(ox_powerplan *p, const void *maps, int where, int nbatch, const double *kfilter, int kwhere, void *out,
+                    int out_where);
+
 /* ---- generic batched c2c FFT on full-plane complex arrays (pixell.fft.fft / ifft, lensing.py:20):
  * out = scale * FFT_direction(in), direction -1 forward / +1 backward, nplanes arrays [ny][nx] */
 int ox_fft_c2c(ox_powerplan *p, const void *in, int where, int nplanes, int direction, double scale, void *out, int out_where);

@@ -138,6 +138,14 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
   for (int iy = tid; iy < LY; iy += NTHREADS) {
     const int my = iy ? a.ny - iy : 0;
     const long long p = (long long)iy * a.nx + ix, q = (long long)my * a.nx + mxp;
+    // covsqrt first: its L2 latency hides behind the Philox / Box-Muller arithmetic below
+    const long long tp = (long long)ix * a.ny + iy, tq = (long long)mxp * a.ny + my;
+    T covp[NC * NC], covq[NC * NC];
+#pragma unroll
+    for (int e = 0; e < NC * NC; e++) {
+      covp[e] = a.covT[(long long)e * n + tp];
+      covq[e] = a.cov_symmetric ? covp[e] : a.covT[(long long)e * n + tq];
+    }
     double pr[NC], pi[NC], qr[NC], qi[NC];
     if (a.mode == OX_NOISE_HOST) {
       const double *base = a.noise + (long long)sim * 2 * NC * n;
@@ -179,14 +187,12 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
     }
     // k(p) = covsqrt(p) r(p), k(p') = covsqrt(p') r(p'); transposed covsqrt: [..][ix][iy]
     double kpr[NC], kpi[NC], kqr[NC], kqi[NC];
-    const long long tp = (long long)ix * a.ny + iy, tq = (long long)mxp * a.ny + my;
 #pragma unroll
     for (int i = 0; i < NC; i++) {
       double sr = 0, si = 0, ur = 0, ui = 0;
 #pragma unroll
       for (int j = 0; j < NC; j++) {
-        double cp = (double)a.covT[(long long)(i * NC + j) * n + tp];
-        double cq = a.cov_symmetric ? cp : (double)a.covT[(long long)(i * NC + j) * n + tq];
+        double cp = (double)covp[i * NC + j], cq = (double)covq[i * NC + j];
         sr += cp * pr[j]; si += cp * pi[j];
         ur += cq * qr[j]; ui += cq * qi[j];
       }

@@ -187,6 +187,24 @@ int forward_half(ox_powerplan *p, const void *maps, int where, int nbatch, const
   return p->fft.exec_r2c(nbatch * p->ncomp, in.p, kh.p);
 }
 
+// maps.filter_map (maps.py:1922-1923): Re(ifft(fft(m) * kfilter)) / Npix with a real full-plane kfilter.
+// For a real map, taking the real part keeps the Hermitian part of k*f, i.e. k(p) * 1/2 [f(p) + f(p')]:
+// one fused multiply between the r2c and c2r transforms, any real filter (beam, l-mask, Wiener).
+template <typename T2>
+__global__ void filter_half_kernel(T2 *__restrict__ kh, const double *__restrict__ f, int ny, int nx, int nxh, double invn) {
+  const long long nh = (long long)ny * nxh;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const long long m = blockIdx.y;
+  const int iy = (int)(i / nxh), ix = (int)(i - (long long)iy * nxh);
+  const int my = iy ? ny - iy : 0, mx = ix ? nx - ix : 0;
+  const double w = 0.5 * (f[(long long)iy * nx + ix] + f[(long long)my * nx + mx]) * invn;
+  T2 z = kh[m * nh + i];
+  z.x = (double)z.x * w;
+  z.y = (double)z.y * w;
+  kh[m * nh + i] = z;
+}
+
 }  // namespace
 
 namespace ox {
@@ -265,6 +283,28 @@ int ox_power_ifft(ox_powerplan *p, const void *kmap, int where, int nbatch, void
   else scale_complex_kernel<float2><<<grid_1d(n, 256), 256, 0, g_stream>>>(p->full1.as<float2>(), n, s);
   OX_KERNEL_CHECK();
   return stage_out(out, out_where, p->full1.p, bytes);
+}
+
+int ox_power_filter(ox_powerplan *p, const void *maps, int where, int nbatch, const double *kfilter, int kwhere, void *out,
+                    int out_where) {
+  OX_REQUIRE(p && maps && kfilter && out, "ox_power_filter: null pointer");
+  OX_REQUIRE(nbatch >= 1 && nbatch <= p->max_batch, "nbatch=%d outside 1..max_batch=%d", nbatch, p->max_batch);
+  ox_geometry *g = p->g;
+  size_t es = elem_size(p->dtype);
+  long long npix = (long long)g->ny * g->nx, nh = (long long)g->ny * g->nxh;
+  const void *fdev;
+  OX_TRY(stage_in(kfilter, kwhere, sizeof(double) * npix, p->window, &fdev));
+  OX_TRY(forward_half(p, maps, where, nbatch, nullptr, p->in1, p->kh1));
+  int planes = nbatch * p->ncomp;
+  dim3 grid((unsigned)((nh + PW_THREADS - 1) / PW_THREADS), planes);
+  double invn = 1.0 / ((double)g->ny * (double)g->nx);
+  if (p->dtype == OX_F64)
+    filter_half_kernel<double2><<<grid, PW_THREADS, 0, g_stream>>>(p->kh1.as<double2>(), (const double *)fdev, g->ny, g->nx, g->nxh, invn);
+  else
+    filter_half_kernel<float2><<<grid, PW_THREADS, 0, g_stream>>>(p->kh1.as<float2>(), (const double *)fdev, g->ny, g->nx, g->nxh, invn);
+  OX_KERNEL_CHECK();
+  OX_TRY(p->fft.exec_c2r(planes, p->kh1.p, p->in1.p));
+  return stage_out(out, out_where, p->in1.p, es * (size_t)planes * npix);
 }
 
 int ox_fft_c2c(ox_powerplan *p, const void *in, int where, int nplanes, int direction, double scale, void *out, int out_where) {

@@ -461,8 +461,14 @@ def mask_kspace(shape, wcs, lxcut=None, lycut=None, lmin=None, lmax=None, method
 def filter_map(imap, kfilter, fc=None):
     """Re(ifft(fft(imap) * kfilter)) / Npix (maps.py:1922-1923)."""
     fc = FourierCalc(imap.shape, imap.wcs) if fc is None else fc
-    k = fc.fft(imap)
-    return ndmap(np.real(fc.ifft(np.asarray(k) * kfilter)), imap.wcs)
+    if np.iscomplexobj(kfilter):
+        raise NotImplementedError("filter_map: complex kfilter is outside the accelerated path")
+    stack, nc = fc._as_stack(imap)
+    kf = np.ascontiguousarray(np.broadcast_to(np.asarray(kfilter, dtype=np.float64), fc.geometry.shape))
+    out = np.empty(stack.shape, dtype=stack.dtype)
+    # one device pass: r2c -> x 1/2[f(l)+f(-l)]/Npix -> c2r (ox_power_filter)
+    check(lib.ox_power_filter(fc._plan(nc), ptr(stack), OX_HOST, 1, ptr(kf), OX_HOST, ptr(out), OX_HOST))
+    return ndmap(out.reshape(np.shape(imap)), getattr(imap, "wcs", fc.wcs))
 
 
 # --------------------------------------------------------------------------- fused pipeline
