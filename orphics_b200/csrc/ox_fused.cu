@@ -134,7 +134,7 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
   const long long n = (long long)a.ny * a.nx;
   const unsigned long long seed = a.mode == OX_NOISE_HOST ? 0ull : (unsigned long long)a.seeds[sim];
   const double h = 0.5 * a.scale;
-#pragma unroll 1
+#pragma unroll 2
   for (int iy = tid; iy < LY; iy += NTHREADS) {
     const int my = iy ? a.ny - iy : 0;
     const long long p = (long long)iy * a.nx + ix, q = (long long)my * a.nx + mxp;
@@ -245,12 +245,23 @@ struct RowArgs {
 template <typename T2, int MX>
 struct PackLoad {
   const T2 *row;  // X[0..MX] in padded shared memory
-  const T2 *tw;   // exp(-2 pi i j / tw_len)
-  int tws_n;      // tw_len / Nx
-  __device__ __forceinline__ T2 operator()(int k, int) const {
+  T2 wu;          // e^{+2 pi i u / Nx} of this thread
+  // k = u + m*NT and NT/Nx = 1/32, so e^{+2 pi i k/Nx} = wu * e^{2 pi i m/32}: the 16 factors are
+  // compile-time constants after unrolling (no table loads: the kernel is L1/shared-memory bound)
+  __device__ __forceinline__ T2 operator()(int k, int m) const {
+    constexpr double C32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                                0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785,
+                                0.0, -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474,
+                                -0.70710678118654752440, -0.83146961230254523708, -0.92387953251128675613, -0.98078528040323044913};
+    constexpr double S32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                                0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913,
+                                1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                                0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785};
     T2 xk = row[pad(k)], xm = row[pad(MX - k)];
-    T2 w = tw[k * tws_n];
-    w.y = -w.y;
+    typedef decltype(xk.x) T;
+    T2 w;
+    w.x = wu.x * (T)C32[m] - wu.y * (T)S32[m];
+    w.y = wu.x * (T)S32[m] + wu.y * (T)C32[m];
     T2 sum = cadd(xk, cconj(xm)), dif = csub(xk, cconj(xm));
     return cadd(sum, mul_i<+1>(cmul(w, dif)));
   }
@@ -307,7 +318,9 @@ fused_row_kernel(RowArgs<T> a) {
     }
     cp_async_wait_all();
     __syncthreads();
-    PackLoad<T2, MX> ld{row, a.tw, tws_n};
+    T2 wu = a.tw[u * tws_n];
+    wu.y = -wu.y;  // e^{+2 pi i u/Nx}
+    PackLoad<T2, MX> ld{row, wu};
     FFT::template run<+1, true, true>(row, tws, u, bar, ld, wst);
   } else {
     // real map rows viewed as z[n] = x[2n] + i x[2n+1]

@@ -225,3 +225,168 @@ class qest(object):
             lib.ox_powerplan_destroy(self._fftplan)
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------
+# callers of the hot path: kappa <-> phi (lensing.py:651-665), Taylens (lensing.py:395-440),
+# FlatLensingSims (lensing.py:458-521)
+def fkappa_to_fphi(fkappa, modlmap):
+    """phi(l) = 2 kappa(l) / (L (L+1)), zero for L < 2 (lensing.py:662-665)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        kmap = np.nan_to_num(2. * fkappa / modlmap / (modlmap + 1.))
+    kmap[modlmap < 2.] = 0.
+    return kmap
+
+
+class _C2C(object):
+    """Batched device c2c transforms of full-plane arrays (ox_fft_c2c) for the callers below."""
+
+    def __init__(self, geometry, nplanes=8):
+        self.geometry = geometry
+        self.npix = geometry.npix
+        self.plan = C.c_void_p()
+        check(lib.ox_powerplan_create(geometry.handle, 1, _capi.OX_F64, nplanes, C.byref(self.plan)))
+
+    def __call__(self, a, inverse=False, scale=None):
+        a = np.ascontiguousarray(a, dtype=np.complex128)
+        out = np.empty_like(a)
+        if scale is None:
+            scale = 1.0 / self.npix if inverse else 1.0
+        check(lib.ox_fft_c2c(self.plan, ptr(a), OX_HOST, a.size // self.npix, 1 if inverse else -1, float(scale), ptr(out), OX_HOST))
+        return out
+
+    def __del__(self):
+        try:
+            lib.ox_powerplan_destroy(self.plan)
+        except Exception:
+            pass
+
+
+def kappa_to_phi(kappa, modlmap, return_fphi=False, _fft=None):
+    """lensing.py:651-657 (enmap.fft/ifft with normalize='phys': the pixel-area factors cancel)."""
+    g = Geometry.get(kappa.shape, kappa.wcs)
+    f = _fft or _C2C(g)
+    fphi = fkappa_to_fphi(f(np.asarray(kappa)), modlmap)
+    phi = ndmap(f(fphi, inverse=True).real, kappa.wcs)
+    return (phi, ndmap(fphi, kappa.wcs)) if return_fphi else phi
+
+
+def flat_taylens(phi, imap, taylor_order=5, _fft=None):
+    """Lens imap by the potential phi with the Taylens algorithm (lensing.py:395-440): nearest-pixel
+    remap plus a Taylor series in the sub-pixel deflection, every derivative an inverse FFT (device)."""
+    from math import factorial, comb
+    g = Geometry.get(phi.shape, phi.wcs)
+    f = _fft or _C2C(g, nplanes=taylor_order + 1)
+    Ny, Nx = g.shape
+    ly_array, lx_array = np.meshgrid(g.ly, g.lx, indexing="ij")
+    kphi = f(np.asarray(phi))
+    alpha = f(np.stack([1j * lx_array * kphi, 1j * ly_array * kphi]), inverse=True).real
+    alphaX, alphaY = alpha
+    iy, ix = np.mgrid[0:Ny, 0:Nx]
+    ext = _enmap.extent(g.shape, phi.wcs, method=g.method)
+    py, px = ext[0] / Ny, ext[1] / Nx
+    alphaX0 = np.array(np.round(alphaX / px), dtype='int64')
+    alphaY0 = np.array(np.round(alphaY / py), dtype='int64')
+    delta_alphaX = alphaX - alphaX0 * px
+    delta_alphaY = alphaY - alphaY0 * py
+    sy, sx = (iy + alphaY0) % Ny, (ix + alphaX0) % Nx
+    lensed = np.asarray(imap)[sy, sx].astype(np.float64)
+    kmap = f(np.asarray(imap))
+    for n in range(1, taylor_order):
+        facs = np.stack([1j ** n * comb(n, k) * lx_array ** (n - k) * ly_array ** k / factorial(n) * kmap for k in range(n + 1)])
+        derivs = f(facs, inverse=True).real
+        for k in range(n + 1):
+            lensed += derivs[k][sy, sx] * delta_alphaX ** (n - k) * delta_alphaY ** k
+    return ndmap(lensed, getattr(imap, "wcs", phi.wcs))
+
+
+def get_central(img, fracy, fracx=None):
+    """maps.get_central (maps.py:1322-1336)."""
+    if fracy is None and fracx is None:
+        return img
+    fracx = fracy if fracx is None else fracx
+    Ny, Nx = img.shape[-2:]
+    cropy, cropx = int(fracy * Ny), int(fracx * Nx)
+    if (cropy % 2 == 0 and Ny % 2 == 1) or (cropy % 2 == 1 and Ny % 2 == 0):
+        cropy -= 1
+    if (cropx % 2 == 0 and Nx % 2 == 1) or (cropx % 2 == 1 and Nx % 2 == 0):
+        cropx -= 1
+    sy, sx = (Ny - cropy) // 2, (Nx - cropx) // 2
+    return img[..., sy:sy + cropy, sx:sx + cropx]
+
+
+class FlatLensingSims(object):
+    """lensing.py:458-521: unlensed GRF -> lensing -> beam -> + noise GRF, every step on the device.
+    The reference remaps with pixell.lensing.displace_map (spline interpolation, out of the path's
+    scope); here the lensing step is the reference's own FFT-based flat_taylens
+    (lensing.py:395-440) with taylor_order = lens_order."""
+
+    def __init__(self, shape, wcs, theory, beam_arcmin, noise_uk_arcmin, noise_e_uk_arcmin=None, noise_b_uk_arcmin=None,
+                 pol=False, fixed_lens_kappa=None):
+        from . import maps, cosmology
+        if len(shape) < 3 and pol:
+            shape = (3,) + tuple(shape)
+        if noise_e_uk_arcmin is None:
+            noise_e_uk_arcmin = np.sqrt(2.) * noise_uk_arcmin
+        if noise_b_uk_arcmin is None:
+            noise_b_uk_arcmin = noise_e_uk_arcmin
+        self.shape, self.wcs = tuple(shape), wcs
+        self.geometry = Geometry.get(shape, wcs)
+        self.modlmap = ndmap(self.geometry.modlmap(), wcs)
+        Ny, Nx = shape[-2:]
+        ells = np.arange(0, self.modlmap.max(), 1)
+        ps_cmb = cosmology.power_from_theory(ells, theory, lensed=False, pol=pol)
+        self.mgen = maps.MapGen(shape, wcs, ps_cmb)
+        self._fft = _C2C(self.geometry, nplanes=8)
+        self._fc = maps.FourierCalc(shape, wcs)
+        if fixed_lens_kappa is not None:
+            self._fixed = True
+            self.update_kappa(fixed_lens_kappa)
+        else:
+            self._fixed = False
+            ps_kk = theory.gCl('kk', self.modlmap).reshape((1, 1, Ny, Nx))
+            self.kgen = maps.MapGen(shape[-2:], wcs, ps_kk)
+            self.ps_kk = ps_kk
+        self.kbeam = maps.gauss_beam(self.modlmap, beam_arcmin)
+        ncomp = 3 if pol else 1
+        ps_noise = np.zeros((ncomp, ncomp, Ny, Nx))
+        ps_noise[0, 0] = (noise_uk_arcmin * np.pi / 180. / 60.) ** 2.
+        if pol:
+            ps_noise[1, 1] = (noise_e_uk_arcmin * np.pi / 180. / 60.) ** 2.
+            ps_noise[2, 2] = (noise_b_uk_arcmin * np.pi / 180. / 60.) ** 2.
+        self.ngen = maps.MapGen(shape, wcs, ps_noise)
+        self.ps_noise = ps_noise
+
+    def update_kappa(self, kappa):
+        self.kappa = kappa
+        self.phi = kappa_to_phi(ndmap(np.asarray(kappa), self.wcs), self.modlmap, _fft=self._fft)
+
+    def get_unlensed(self, seed=None):
+        return self.mgen.get_map(seed=seed)
+
+    def get_kappa(self, seed=None):
+        return self.kgen.get_map(seed=seed)
+
+    def get_sim(self, seed_cmb=None, seed_kappa=None, seed_noise=None, lens_order=5, return_intermediate=False,
+                skip_lensing=False, cfrac=None):
+        from . import maps
+        unlensed = self.get_unlensed(seed_cmb)
+        if skip_lensing:
+            lensed = unlensed
+            kappa = ndmap(np.asarray(lensed).reshape((-1,) + self.geometry.shape)[0] * 0, self.wcs)
+        else:
+            if not (self._fixed):
+                kappa = self.get_kappa(seed_kappa)
+                self.update_kappa(kappa)
+            else:
+                kappa = None
+                assert seed_kappa is None
+            comps = np.asarray(unlensed).reshape((-1,) + self.geometry.shape)
+            lensed = np.stack([flat_taylens(self.phi, ndmap(c, self.wcs), taylor_order=lens_order, _fft=self._fft) for c in comps])
+            lensed = ndmap(lensed.reshape(np.shape(unlensed)), self.wcs)
+        beamed = maps.filter_map(lensed, self.kbeam, self._fc)
+        noise_map = self.ngen.get_map(seed=seed_noise)
+        observed = ndmap(np.asarray(beamed) + np.asarray(noise_map), self.wcs)
+        if return_intermediate:
+            return [get_central(x, cfrac) if x is not None else None for x in [unlensed, kappa, lensed, beamed, noise_map, observed]]
+        return get_central(observed, cfrac)

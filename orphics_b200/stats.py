@@ -296,3 +296,40 @@ class Statistics:
         if label not in self._stack:
             raise KeyError(f"{label!r} is not a stack-mode label.")
         return self._stack[label]
+
+    # checkpoint format of the reference (stats.py:1455-1530): .npz with keys
+    # stats/<label>/{N,SUM,CROSS} and stack/<label>/SUM, written by the root rank only
+    def save_reduced(self, path, compressed=False, root_rank=0):
+        self._check()
+        if self.mpi_enabled:
+            import torch.distributed as dist
+            group = None if self.comm is True else self.comm
+            if dist.get_rank(group) != root_rank:
+                return
+        arrays = {}
+        for lab in self._sum:
+            arrays[f"stats/{lab}/N"] = np.array(self._n[lab], dtype=np.int64)
+            arrays[f"stats/{lab}/SUM"] = self._sum[lab]
+            arrays[f"stats/{lab}/CROSS"] = self._cross[lab]
+        for lab in self._stack:
+            arrays[f"stack/{lab}/SUM"] = self._stack[lab]
+        (np.savez_compressed if compressed else np.savez)(path, **arrays)
+
+    @classmethod
+    def load_reduced(cls, path, comm=None, dtype=np.float64):
+        data = np.load(path, allow_pickle=False)
+        acc = cls(comm=comm, dtype=dtype)
+        for key in data.files:
+            kind, lab, what = key.split("/")
+            if kind == "stats":
+                if what == "N":
+                    acc._n[lab] = int(data[key])
+                elif what == "SUM":
+                    acc._sum[lab] = np.array(data[key])
+                elif what == "CROSS":
+                    acc._cross[lab] = np.array(data[key])
+            elif kind == "stack" and what == "SUM":
+                acc._stack[lab] = np.array(data[key])
+                acc._k.setdefault(lab, 0)     # the reference does not store the stack count either
+        acc._reduced = True
+        return acc

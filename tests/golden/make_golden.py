@@ -98,3 +98,13 @@ np.savez_compressed(os.path.join(here, "mpi_distribute.npz"),
                     **{f"n_{n}_{c}": rmpi.mpi_distribute(n, c)[0] for n, c in cases},
                     **{f"first_{n}_{c}": np.array([t[0] for t in rmpi.mpi_distribute(n, c)[1]]) for n, c in cases})
 print("done")
+
+# the reference's own checkpoint file (stats.py:1455-1484) for the P=2 case above
+s = rstats.Statistics(comm=None)
+z = np.load(os.path.join(here, "statistics_P2.npz"))
+for r in range(2):
+    s.extend("bandpowers", z[f"x{r}"])
+s.add_stack("meanfield", np.arange(12.).reshape(3, 4))
+s.allreduce()
+s.save_reduced(os.path.join(here, "statistics_reduced_ref.npz"))
+print("saved reference-format checkpoint")

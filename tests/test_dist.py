@@ -91,3 +91,29 @@ def test_single_process_statistics_matches_reference_golden():
         np.testing.assert_allclose(s.mean("v"), z["mean"], rtol=1e-14)
         np.testing.assert_allclose(s.cov("v"), z["cov"], rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose(s.var("v"), z["var"], rtol=1e-12, atol=1e-14)
+
+
+def test_statistics_checkpoint_format_matches_reference(tmp_path):
+    """save_reduced/load_reduced use the reference's .npz key layout (stats.py:1455-1530):
+    a file written by the reference loads here, and our file has the same keys and arrays."""
+    from conftest import GOLDEN, load_golden
+    from orphics_b200 import stats
+    ref = np.load(os.path.join(GOLDEN, "statistics_reduced_ref.npz"))
+    s = stats.Statistics.load_reduced(os.path.join(GOLDEN, "statistics_reduced_ref.npz"))
+    z = load_golden("statistics_P2.npz")
+    assert s.count("bandpowers") == int(z["N"])
+    np.testing.assert_allclose(s.mean("bandpowers"), z["mean"], rtol=1e-14)
+    np.testing.assert_allclose(s.cov("bandpowers"), z["cov"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_array_equal(s.stack_sum("meanfield"), np.arange(12.).reshape(3, 4))
+    mine = stats.Statistics()
+    for r in range(2):
+        mine.extend("bandpowers", z[f"x{r}"])
+    mine.add_stack("meanfield", np.arange(12.).reshape(3, 4))
+    mine.allreduce()
+    out = tmp_path / "ours.npz"
+    mine.save_reduced(out)
+    ours = np.load(out)
+    assert sorted(ours.files) == sorted(ref.files)
+    for k in ref.files:
+        assert ours[k].dtype == ref[k].dtype and ours[k].shape == ref[k].shape
+        np.testing.assert_allclose(ours[k], ref[k], rtol=1e-13)
