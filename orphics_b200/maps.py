@@ -53,6 +53,19 @@ def _eigpow(A, e):
         a = A[0, 0]
         with np.errstate(invalid="ignore", divide="ignore"):
             return np.where(a > 0, np.abs(a) ** e, 0.0)[None, None]
+    n = A.shape[0]
+    offdiag = ~np.eye(n, dtype=bool)
+    if not A[offdiag].any():
+        # diagonal matrices (e.g. white-noise spectra, lensing.py:482-487): eigenvalues are the diagonal
+        D = np.stack([A[i, i] for i in range(n)])
+        emax = np.max(np.abs(D), 0, keepdims=True)
+        bad = (D < emax * np.finfo(np.float64).resolution * 100) | (D < np.finfo(np.float64).tiny * 1e4)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            De = np.where(bad, 0.0, np.abs(D) ** e)
+        out = np.zeros_like(A)
+        for i in range(n):
+            out[i, i] = De[i]
+        return out
     M = np.moveaxis(A, (0, 1), (-2, -1))
     E, V = np.linalg.eigh(M)
     emax = np.max(np.abs(E), -1, keepdims=True)
