@@ -25,6 +25,7 @@
 
 #include "ox_common.cuh"
 #include "ox_fft.cuh"
+#include "ox_rng.cuh"
 
 using namespace ox;
 using namespace oxfft;
@@ -32,34 +33,6 @@ using namespace oxfft;
 namespace {
 
 // ---- shared helpers -------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; r++) {
-    unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
-  }
-  return c;
-}
-
-__device__ __forceinline__ void philox_normal2(unsigned long long seed, unsigned long long pix, unsigned comp,
-                                               unsigned stream, double &n1, double &n2) {
-  uint4 x = philox4x32_10(make_uint4((unsigned)pix, (unsigned)(pix >> 32), comp, stream),
-                          make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
-  unsigned long long a = ((unsigned long long)x.x << 32) | x.y;
-  unsigned long long b = ((unsigned long long)x.z << 32) | x.w;
-  double u1 = (double)((a >> 11) + 1ull) * 0x1.0p-53;
-  double u2 = (double)(b >> 11) * 0x1.0p-53;
-  double r = sqrt(-2.0 * log(u1));
-  double s, co;
-  sincospi(2.0 * u2, &s, &co);
-  n1 = r * co;
-  n2 = r * s;
-}
-
 __device__ __forceinline__ void rot_cs(double y, double x, double sgn, double &c, double &s) {
   double l2 = y * y + x * x;
   c = 1.0;
@@ -111,7 +84,7 @@ struct SimColArgs {
   const typename V2<T>::type *tw;  // exp(-2 pi i j / tw_len)
   int tw_len;
   int ny, nx, mx;  // mx = nx/2
-  int mode, rot, cov_symmetric;
+  int rot, cov_symmetric;
   double scale, rot_sgn;
 };
 
@@ -121,111 +94,142 @@ struct GlobalStore {
   __device__ __forceinline__ void operator()(int f, T2 v, int) const { dst[f] = v; }
 };
 
-template <typename T, int LY, int NC>
+// first-stage input held in registers (m is a compile-time constant after unrolling)
+template <typename T2>
+struct RegLoad {
+  const T2 *v;
+  __device__ __forceinline__ T2 operator()(int, int m) const { return v[m]; }
+};
+
+// Hermitian part of the simulated Fourier field at pixel (iy, ix) of the half plane:
+// z[c] = 1/2 [k_c(p) + conj k_c(p')] / sqrt(N), k = covsqrt . r [rotated EB -> QU]
+// (MapGen.get_map, maps.py:1576-1587, followed by enmap.ifft(...).real)
+template <typename T, int NC, int MODE>
+__device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::PhiloxKeys &keys, const double2 *logtab,
+                                          const double *noise_sim, int ix, int mxp, int iy, double h,
+                                          typename V2<T>::type (&z)[NC]) {
+  const int my = iy ? a.ny - iy : 0;
+  const unsigned n = (unsigned)a.ny * (unsigned)a.nx;
+  const unsigned p = (unsigned)iy * a.nx + ix, q = (unsigned)my * a.nx + mxp;
+  const unsigned tp = (unsigned)ix * a.ny + iy, tq = (unsigned)mxp * a.ny + my;
+  T covp[NC * NC], covq[NC * NC];
+#pragma unroll
+  for (int e = 0; e < NC * NC; e++) {
+    covp[e] = a.covT[(size_t)e * n + tp];
+    covq[e] = a.cov_symmetric ? covp[e] : a.covT[(size_t)e * n + tq];
+  }
+  double pr[NC], pi[NC], qr[NC], qi[NC];
+  if (MODE == OX_NOISE_HOST) {
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      pr[c] = noise_sim[(size_t)c * n + p];
+      pi[c] = noise_sim[(size_t)(NC + c) * n + p];
+      qr[c] = noise_sim[(size_t)c * n + q];
+      qi[c] = noise_sim[(size_t)(NC + c) * n + q];
+    }
+  } else if (MODE == OX_NOISE_PHILOX) {
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      oxrng::box_muller_fast(oxrng::philox4x32_10(make_uint4(p, 0u, c, 0u), keys), logtab, pr[c], pi[c]);
+      // (the self-conjugate pixels draw twice: same counter, same value)
+      oxrng::box_muller_fast(oxrng::philox4x32_10(make_uint4(q, 0u, c, 0u), keys), logtab, qr[c], qi[c]);
+    }
+  } else {
+    const bool conj_me = q < p, selfc = q == p;
+    const unsigned canon = conj_me ? q : p;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      double n1, n2;
+      oxrng::box_muller_fast(oxrng::philox4x32_10(make_uint4(canon, 0u, c, 1u), keys), logtab, n1, n2);
+      pr[c] = selfc ? n1 : n1 * 0.70710678118654752440;
+      pi[c] = selfc ? 0.0 : (conj_me ? -n2 : n2) * 0.70710678118654752440;
+      qr[c] = pr[c];
+      qi[c] = -pi[c];
+    }
+  }
+  // k(p) = covsqrt(p) r(p), k(p') = covsqrt(p') r(p')
+  double kpr[NC], kpi[NC], kqr[NC], kqi[NC];
+#pragma unroll
+  for (int i = 0; i < NC; i++) {
+    double sr = 0, si = 0, ur = 0, ui = 0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      double cp = (double)covp[i * NC + j], cq = (double)covq[i * NC + j];
+      sr += cp * pr[j]; si += cp * pi[j];
+      ur += cq * qr[j]; ui += cq * qi[j];
+    }
+    kpr[i] = sr; kpi[i] = si; kqr[i] = ur; kqi[i] = ui;
+  }
+  if (NC == 3 && a.rot) {
+    // inverse queb_rotmat: [Q;U] = [[c, s],[-s, c]] [E;B], each pixel with its own angle
+    double c, sn;
+    rot_cs(a.ly[iy], a.lx[ix], a.rot_sgn, c, sn);
+    double t1 = c * kpr[1] + sn * kpr[2], t2 = c * kpi[1] + sn * kpi[2];
+    double t3 = -sn * kpr[1] + c * kpr[2], t4 = -sn * kpi[1] + c * kpi[2];
+    kpr[1] = t1; kpi[1] = t2; kpr[2] = t3; kpi[2] = t4;
+    rot_cs(a.ly[my], a.lx[mxp], a.rot_sgn, c, sn);
+    t1 = c * kqr[1] + sn * kqr[2]; t2 = c * kqi[1] + sn * kqi[2];
+    t3 = -sn * kqr[1] + c * kqr[2]; t4 = -sn * kqi[1] + c * kqi[2];
+    kqr[1] = t1; kqi[1] = t2; kqr[2] = t3; kqi[2] = t4;
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    z[c].x = (T)(h * (kpr[c] + kqr[c]));
+    z[c].y = (T)(h * (kpi[c] - kqi[c]));
+  }
+}
+
+template <typename T, int LY, int NC, int MODE>
 __global__ void __launch_bounds__(NC *(LY / 16))
 fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[nsim][NC][mx+1][ny]*/) {
   typedef typename V2<T>::type T2;
   typedef BlockFFT<T, LY> FFT;
   constexpr int NT = FFT::NT, NTHREADS = NC * NT, PS = padded_size(LY);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T2 *s = reinterpret_cast<T2 *>(smem_raw);  // [NC][PS]
+  T2 *s = reinterpret_cast<T2 *>(smem_raw);                                        // [NC][PS]
+  double2 *logtab = reinterpret_cast<double2 *>(smem_raw + sizeof(T2) * NC * PS);  // [129]
   const int ix = blockIdx.x, sim = blockIdx.y, tid = threadIdx.x;
   const int mxp = ix ? a.nx - ix : 0;  // mirrored column
-  const long long n = (long long)a.ny * a.nx;
-  const unsigned long long seed = a.mode == OX_NOISE_HOST ? 0ull : (unsigned long long)a.seeds[sim];
   const double h = 0.5 * a.scale;
-#pragma unroll 2
-  for (int iy = tid; iy < LY; iy += NTHREADS) {
-    const int my = iy ? a.ny - iy : 0;
-    const long long p = (long long)iy * a.nx + ix, q = (long long)my * a.nx + mxp;
-    // covsqrt first: its L2 latency hides behind the Philox / Box-Muller arithmetic below
-    const long long tp = (long long)ix * a.ny + iy, tq = (long long)mxp * a.ny + my;
-    T covp[NC * NC], covq[NC * NC];
-#pragma unroll
-    for (int e = 0; e < NC * NC; e++) {
-      covp[e] = a.covT[(long long)e * n + tp];
-      covq[e] = a.cov_symmetric ? covp[e] : a.covT[(long long)e * n + tq];
-    }
-    double pr[NC], pi[NC], qr[NC], qi[NC];
-    if (a.mode == OX_NOISE_HOST) {
-      const double *base = a.noise + (long long)sim * 2 * NC * n;
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        pr[c] = base[(long long)c * n + p];
-        pi[c] = base[(long long)(NC + c) * n + p];
-        qr[c] = base[(long long)c * n + q];
-        qi[c] = base[(long long)(NC + c) * n + q];
-      }
-    } else if (a.mode == OX_NOISE_PHILOX) {
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        philox_normal2(seed, (unsigned long long)p, c, 0u, pr[c], pi[c]);
-        if (q == p) {
-          qr[c] = pr[c];
-          qi[c] = pi[c];
-        } else {
-          philox_normal2(seed, (unsigned long long)q, c, 0u, qr[c], qi[c]);
-        }
-      }
-    } else {
-      const bool conj_me = q < p;
-      const long long canon = conj_me ? q : p;
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        double n1, n2;
-        philox_normal2(seed, (unsigned long long)canon, c, 1u, n1, n2);
-        if (q == p) {
-          pr[c] = n1;
-          pi[c] = 0.0;
-        } else {
-          pr[c] = n1 * 0.70710678118654752440;
-          pi[c] = (conj_me ? -n2 : n2) * 0.70710678118654752440;
-        }
-        qr[c] = pr[c];
-        qi[c] = -pi[c];
-      }
-    }
-    // k(p) = covsqrt(p) r(p), k(p') = covsqrt(p') r(p'); transposed covsqrt: [..][ix][iy]
-    double kpr[NC], kpi[NC], kqr[NC], kqi[NC];
-#pragma unroll
-    for (int i = 0; i < NC; i++) {
-      double sr = 0, si = 0, ur = 0, ui = 0;
-#pragma unroll
-      for (int j = 0; j < NC; j++) {
-        double cp = (double)covp[i * NC + j], cq = (double)covq[i * NC + j];
-        sr += cp * pr[j]; si += cp * pi[j];
-        ur += cq * qr[j]; ui += cq * qi[j];
-      }
-      kpr[i] = sr; kpi[i] = si; kqr[i] = ur; kqi[i] = ui;
-    }
-    if (NC == 3 && a.rot) {
-      // inverse queb_rotmat: [Q;U] = [[c, s],[-s, c]] [E;B], each pixel with its own angle
-      double c, sn;
-      rot_cs(a.ly[iy], a.lx[ix], a.rot_sgn, c, sn);
-      double t1 = c * kpr[1] + sn * kpr[2], t2 = c * kpi[1] + sn * kpi[2];
-      double t3 = -sn * kpr[1] + c * kpr[2], t4 = -sn * kpi[1] + c * kpi[2];
-      kpr[1] = t1; kpi[1] = t2; kpr[2] = t3; kpi[2] = t4;
-      rot_cs(a.ly[my], a.lx[mxp], a.rot_sgn, c, sn);
-      t1 = c * kqr[1] + sn * kqr[2]; t2 = c * kqi[1] + sn * kqi[2];
-      t3 = -sn * kqr[1] + c * kqr[2]; t4 = -sn * kqi[1] + c * kqi[2];
-      kqr[1] = t1; kqi[1] = t2; kqr[2] = t3; kqi[2] = t4;
-    }
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      T2 z;
-      z.x = (T)(h * (kpr[c] + kqr[c]));
-      z.y = (T)(h * (kpi[c] - kqi[c]));
-      s[c * PS + pad(iy)] = z;
-    }
+  oxrng::PhiloxKeys keys;
+  const double *noise_sim = nullptr;
+  if (MODE == OX_NOISE_HOST) {
+    noise_sim = a.noise + (size_t)sim * 2 * NC * a.ny * a.nx;
+  } else {
+    keys.init((unsigned long long)a.seeds[sim]);
+    oxrng::load_log_table(logtab, tid, NTHREADS);
+    __syncthreads();
   }
-  __syncthreads();
   const int f = tid / NT, u = tid - f * NT;
   typename FFT::Twiddles tws;
   tws.init(a.tw, a.tw_len / LY, u);
-  const int bar = (NC > 1 && NT % 32 == 0) ? 1 + f : 0;
-  SmemLoad<T2> ld{s + f * PS};
-  GlobalStore<T2> st{Ht + (((long long)sim * NC + f) * (a.mx + 1) + ix) * a.ny};
-  FFT::template run<+1, true, false>(s + f * PS, tws, u, bar, ld, st);
+  GlobalStore<T2> st{Ht + (((size_t)sim * NC + f) * (a.mx + 1) + ix) * a.ny};
+  if (NC == 1) {
+    // T-only: a thread generates exactly the 16 inputs u + m*NT of its first radix-16 butterfly:
+    // straight-line code (16 independent Philox/Box-Muller chains for the scheduler to interleave),
+    // no staging in shared memory
+    T2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      T2 z[NC];
+      sim_pixel<T, NC, MODE>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);
+      v[m] = z[0];
+    }
+    RegLoad<T2> ld{v};
+    FFT::template run<+1, false, false>(s, tws, u, 0, ld, st);
+  } else {
+#pragma unroll 2
+    for (int iy = tid; iy < LY; iy += NTHREADS) {
+      T2 z[NC];
+      sim_pixel<T, NC, MODE>(a, keys, logtab, noise_sim, ix, mxp, iy, h, z);
+#pragma unroll
+      for (int c = 0; c < NC; c++) s[c * PS + pad(iy)] = z[c];
+    }
+    __syncthreads();
+    const int bar = (NT % 32 == 0) ? 1 + f : 0;
+    SmemLoad<T2> ld{s + f * PS};
+    FFT::template run<+1, true, false>(s + f * PS, tws, u, bar, ld, st);
+  }
 }
 
 // ---- K_B -------------------------------------------------------------------------------
@@ -267,21 +271,23 @@ struct PackLoad {
   }
 };
 
-// last-stage output of the c2r transform: z[n] = x[2n] + i x[2n+1]; store the map, apply the taper
-template <typename T, int MX>
-struct WindowStore {
+// last-stage output of the c2r transform: z[n] = x[2n] + i x[2n+1]; store the map, apply the taper and
+// KEEP the element in registers: the outputs u + m*NT of a thread's last stage are exactly the inputs
+// of its first forward butterfly, so the real-space row never goes back to shared memory
+template <typename T>
+struct WindowKeep {
   typedef typename V2<T>::type T2;
-  T2 *row;           // shared
+  T2 *keep;          // registers [16]
   T2 *map_row;       // global or null
   const T2 *win_row; // global or null
-  __device__ __forceinline__ void operator()(int n, T2 z, int) const {
+  __device__ __forceinline__ void operator()(int n, T2 z, int m) const {
     if (map_row) map_row[n] = z;
     if (win_row) {
       T2 w = win_row[n];
       z.x *= w.x;
       z.y *= w.y;
     }
-    row[pad(n)] = z;
+    keep[m] = z;
   }
 };
 
@@ -305,8 +311,9 @@ fused_row_kernel(RowArgs<T> a) {
   // the NT threads of one row synchronise among themselves only (named barriers need whole warps)
   const int bar = (NT % 32 == 0) ? 1 + f : 0;
   const long long rowoff = (long long)(iy0 + f) * MX;
-  WindowStore<T, MX> wst;
-  wst.row = row;
+  T2 keep[16];
+  WindowKeep<T> wst;
+  wst.keep = keep;
   wst.map_row = a.map_out ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
   wst.win_row = a.window ? reinterpret_cast<const T2 *>(a.window) + rowoff : nullptr;
   if (a.Hin) {
@@ -321,7 +328,7 @@ fused_row_kernel(RowArgs<T> a) {
     T2 wu = a.tw[u * tws_n];
     wu.y = -wu.y;  // e^{+2 pi i u/Nx}
     PackLoad<T2, MX> ld{row, wu};
-    FFT::template run<+1, true, true>(row, tws, u, bar, ld, wst);
+    FFT::template run<+1, true, false>(row, tws, u, bar, ld, wst);
   } else {
     // real map rows viewed as z[n] = x[2n] + i x[2n+1]
     const T2 *src = reinterpret_cast<const T2 *>(a.map_in + (plane * a.ny + iy0 + f) * (long long)NX);
@@ -330,24 +337,35 @@ fused_row_kernel(RowArgs<T> a) {
       const int n = u + m * NT;
       wst(n, src[n], m);
     }
-    fft_sync(bar, NT);
   }
   if (!a.Hout) return;
-  FFT::template run_inplace<-1>(row, tws, u, bar);
+  {
+    // forward transform fed from registers; IN_SMEM = true: the other threads of the row may still be
+    // reading the inverse transform's last exchange, so the first stage synchronises before it writes
+    RegLoad<T2> ld{keep};
+    SmemStore<T2> st{row};
+    FFT::template run<-1, true, true>(row, tws, u, bar, ld, st);
+  }
   __syncthreads();
-  // transposed store with the r2c unpacking fused in:
-  // X[k] = 1/2 [(Z[k] + conj Z[M-k]) - i e^{-2 pi i k/Nx} (Z[k] - conj Z[M-k])], k = 0..M, Z[M] = Z[0]
+  // transposed store with the r2c unpacking fused in, two outputs per pair (k, M-k) of inputs:
+  //   X[k]   = 1/2 [(Z[k] + conj Z[M-k]) - i w_k (Z[k] - conj Z[M-k])],  w_k = e^{-2 pi i k/Nx}
+  //   X[M-k] = 1/2 conj[(Z[k] + conj Z[M-k]) + i w_k (Z[k] - conj Z[M-k])]      (w_{M-k} = -conj w_k)
+  // with Z[M] = Z[0]; k = 0 yields X[0] and the Nyquist column X[M]
   T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + iy0;
-  for (int e = tid; e < (MX + 1) * R; e += NTHREADS) {
+  for (int e = tid; e < (MX / 2 + 1) * R; e += NTHREADS) {
     int k = e / R, r = e - k * R;
     const T2 *zr = s + r * PS;
-    T2 zk = zr[pad(k == MX ? 0 : k)], zm = zr[pad(k == 0 ? 0 : MX - k)];
+    T2 zk = zr[pad(k)], zm = zr[pad(k == 0 ? 0 : MX - k)];
     T2 w = a.tw[k * tws_n];
     T2 sum = cadd(zk, cconj(zm)), dif = csub(zk, cconj(zm));
-    T2 x = cadd(sum, mul_i<-1>(cmul(w, dif)));
-    x.x *= (T)0.5;
-    x.y *= (T)0.5;
-    dst[(long long)k * a.ny + r] = x;
+    T2 pw = mul_i<+1>(cmul(w, dif));
+    T2 x0, x1;
+    x0.x = (T)0.5 * (sum.x - pw.x);
+    x0.y = (T)0.5 * (sum.y - pw.y);
+    x1.x = (T)0.5 * (sum.x + pw.x);
+    x1.y = -(T)0.5 * (sum.y + pw.y);
+    dst[(long long)k * a.ny + r] = x0;
+    if (2 * k != MX) dst[(long long)(MX - k) * a.ny + r] = x1;
   }
 }
 
@@ -545,17 +563,28 @@ int set_smem(F kernel, size_t bytes) {
 
 constexpr size_t SMEM_MAX = 227 * 1024;
 
-template <typename T, int LY, int NC>
-int launch_sim_col(SimColArgs<T> &a, void *Ht, int nsim) {
+template <typename T, int LY, int NC, int MODE>
+int launch_sim_col_mode(SimColArgs<T> &a, void *Ht, int nsim) {
   typedef typename V2<T>::type T2;
-  size_t smem = sizeof(T2) * NC * padded_size(LY);
+  size_t smem = sizeof(T2) * NC * padded_size(LY) + sizeof(double2) * oxrng::LOG_TABLE_ENTRIES;
   OX_REQUIRE(smem <= SMEM_MAX, "fused sim: column of %d x %d comps needs %zu B of shared memory", LY, NC, smem);
-  auto k = fused_sim_col_kernel<T, LY, NC>;
+  auto k = fused_sim_col_kernel<T, LY, NC, MODE>;
   OX_TRY(set_smem(k, smem));
   dim3 grid(a.mx + 1, nsim);
   k<<<grid, NC * (LY / 16), smem, g_stream>>>(a, (T2 *)Ht);
   OX_KERNEL_CHECK();
   return OX_OK;
+}
+
+template <typename T, int LY, int NC>
+int launch_sim_col(SimColArgs<T> &a, void *Ht, int nsim, int mode) {
+  switch (mode) {
+    case OX_NOISE_HOST: return launch_sim_col_mode<T, LY, NC, OX_NOISE_HOST>(a, Ht, nsim);
+    case OX_NOISE_PHILOX: return launch_sim_col_mode<T, LY, NC, OX_NOISE_PHILOX>(a, Ht, nsim);
+    case OX_NOISE_PHILOX_HERMITIAN: return launch_sim_col_mode<T, LY, NC, OX_NOISE_PHILOX_HERMITIAN>(a, Ht, nsim);
+  }
+  set_error("fused sim: unknown noise mode %d", mode);
+  return OX_ERR_INVALID;
 }
 
 template <typename T, int LY, int NC>
@@ -692,7 +721,6 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
   sa.tw = fs.tw.as<T2>();
   sa.tw_len = fs.tw_len;
   sa.ny = g->ny; sa.nx = g->nx; sa.mx = g->nx / 2;
-  sa.mode = noise_mode;
   sa.rot = (flags & OX_FLAG_ROT) ? 1 : 0;
   sa.cov_symmetric = fs.cov_symmetric ? 1 : 0;
   sa.scale = 1.0 / sqrt((double)g->ny * (double)g->nx);
@@ -700,7 +728,7 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
   int st = OX_ERR_UNSUPPORTED;
 #define OX_SIMCOL(LY)                                                                     \
   case LY:                                                                                \
-    st = nc == 1 ? launch_sim_col<T, LY, 1>(sa, fs.Ha.p, nsim) : launch_sim_col<T, LY, 3>(sa, fs.Ha.p, nsim); \
+    st = nc == 1 ? launch_sim_col<T, LY, 1>(sa, fs.Ha.p, nsim, noise_mode) : launch_sim_col<T, LY, 3>(sa, fs.Ha.p, nsim, noise_mode); \
     break;
   switch (g->ny) {
     OX_SIMCOL(256) OX_SIMCOL(512) OX_SIMCOL(1024) OX_SIMCOL(2048) OX_SIMCOL(4096)
