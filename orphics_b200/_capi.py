@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liborphx.so")
+# ORPHX_LIB: alternative build of the same library (kernel-tuning experiments, tools/sweep_variants.sh)
+LIB_PATH = os.environ.get("ORPHX_LIB") or os.path.join(_HERE, "_lib", "liborphx.so")
 
 OX_F64, OX_F32 = 0, 1
 OX_HOST, OX_DEVICE = 0, 1

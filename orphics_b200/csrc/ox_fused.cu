@@ -30,7 +30,24 @@
 using namespace ox;
 using namespace oxfft;
 
+// compile-time tuning knobs (defaults = the measured best on B200, profiles/r01_variants.txt)
+#ifndef OX_KA_REGS
+#define OX_KA_REGS 0   // register cap per thread asked of K_A (T-only), 0 = none
+#endif
+#ifndef OX_KB_ROWS64
+#define OX_KB_ROWS64 4  // rows per CTA of K_B for 16-byte elements (64 B segments)
+#endif
+#ifndef OX_KC_REGS
+#define OX_KC_REGS 128   // register cap per thread asked of K_C (T-only), 0 = none
+#endif
+#ifndef OX_KC_COLS
+#define OX_KC_COLS 8    // columns per CTA of K_C
+#endif
+
 namespace {
+
+// min resident CTAs per SM that caps the registers per thread at `regs` (0 = no cap)
+constexpr int minb_for(int threads, int regs) { return regs > 0 && 65536 / (threads * regs) > 1 ? 65536 / (threads * regs) : 1; }
 
 // ---- shared helpers -------------------------------------------------------------------
 __device__ __forceinline__ void rot_cs(double y, double x, double sgn, double &c, double &s) {
@@ -52,6 +69,10 @@ __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// load through the read-only (non-coherent) path: the compiler may reorder it across stores
+__device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
+__device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
 
 // deterministic in-warp reduce-by-key: afterwards the lowest lane of every group of equal keys
 // holds the group's sums (fixed shuffle tree, see ox_binner.cu)
@@ -104,7 +125,9 @@ struct RegLoad {
 // Hermitian part of the simulated Fourier field at pixel (iy, ix) of the half plane:
 // z[c] = 1/2 [k_c(p) + conj k_c(p')] / sqrt(N), k = covsqrt . r [rotated EB -> QU]
 // (MapGen.get_map, maps.py:1576-1587, followed by enmap.ifft(...).real)
-template <typename T, int NC, int MODE>
+// INTERIOR: the column is neither ix = 0 nor the Nyquist column, so no pixel is its own mirror image
+// and the canonical member of each pair {p, p'} is decided by the row alone
+template <typename T, int NC, int MODE, bool INTERIOR>
 __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::PhiloxKeys &keys, const double2 *logtab,
                                           const double *noise_sim, int ix, int mxp, int iy, double h,
                                           typename V2<T>::type (&z)[NC]) {
@@ -135,7 +158,7 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
       oxrng::box_muller_fast(oxrng::philox4x32_10(make_uint4(q, 0u, c, 0u), keys), logtab, qr[c], qi[c]);
     }
   } else {
-    const bool conj_me = q < p, selfc = q == p;
+    const bool conj_me = INTERIOR ? iy > (a.ny >> 1) : q < p, selfc = INTERIOR ? false : q == p;
     const unsigned canon = conj_me ? q : p;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
@@ -180,7 +203,7 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
 }
 
 template <typename T, int LY, int NC, int MODE>
-__global__ void __launch_bounds__(NC *(LY / 16))
+__global__ void __launch_bounds__(NC *(LY / 16), (NC == 1 ? minb_for(LY / 16, OX_KA_REGS) : 1))
 fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[nsim][NC][mx+1][ny]*/) {
   typedef typename V2<T>::type T2;
   typedef BlockFFT<T, LY> FFT;
@@ -209,11 +232,20 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
     // straight-line code (16 independent Philox/Box-Muller chains for the scheduler to interleave),
     // no staging in shared memory
     T2 v[16];
+    if (ix != 0 && ix != a.mx) {
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-      T2 z[NC];
-      sim_pixel<T, NC, MODE>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);
-      v[m] = z[0];
+      for (int m = 0; m < 16; m++) {
+        T2 z[NC];
+        sim_pixel<T, NC, MODE, true>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);
+        v[m] = z[0];
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        T2 z[NC];
+        sim_pixel<T, NC, MODE, false>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);
+        v[m] = z[0];
+      }
     }
     RegLoad<T2> ld{v};
     FFT::template run<+1, false, false>(s, tws, u, 0, ld, st);
@@ -221,7 +253,7 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
 #pragma unroll 2
     for (int iy = tid; iy < LY; iy += NTHREADS) {
       T2 z[NC];
-      sim_pixel<T, NC, MODE>(a, keys, logtab, noise_sim, ix, mxp, iy, h, z);
+      sim_pixel<T, NC, MODE, false>(a, keys, logtab, noise_sim, ix, mxp, iy, h, z);
 #pragma unroll
       for (int c = 0; c < NC; c++) s[c * PS + pad(iy)] = z[c];
     }
@@ -283,7 +315,7 @@ struct WindowKeep {
   __device__ __forceinline__ void operator()(int n, T2 z, int m) const {
     if (map_row) map_row[n] = z;
     if (win_row) {
-      T2 w = win_row[n];
+      T2 w = ldg2(win_row + n);  // read-only path: may be hoisted above the map stores of earlier elements
       z.x *= w.x;
       z.y *= w.y;
     }
@@ -319,9 +351,22 @@ fused_row_kernel(RowArgs<T> a) {
   if (a.Hin) {
     // tile load: for each ix the R rows are R*16 B contiguous in the transposed layout
     const T2 *src = a.Hin + plane * (long long)(MX + 1) * a.ny + iy0;
-    for (int e = tid; e < (MX + 1) * R; e += NTHREADS) {
-      int ix = e / R, r = e - ix * R;
-      cp_async<sizeof(T2)>(&s[r * PS + pad(ix)], &src[(long long)ix * a.ny + r]);
+    // (unrolled with constant strides: a loop that bumps the address registers stalls every
+    // iteration on the write-after-read scoreboard of the previous LDGSTS)
+    if constexpr ((NTHREADS / R) % 16 == 0 && (MX * R) % NTHREADS == 0) {
+      constexpr int IXS = NTHREADS / R;  // ix advance per iteration; pad(ix + IXS) = pad(ix) + pad(IXS)
+      const int ix0 = tid / R, r = tid - ix0 * R;
+      T2 *sdst = &s[r * PS + pad(ix0)];
+      const T2 *gsrc = &src[(long long)ix0 * a.ny + r];
+      const long long gstride = (long long)IXS * a.ny;
+#pragma unroll
+      for (int i = 0; i < MX * R / NTHREADS; i++) cp_async<sizeof(T2)>(sdst + i * pad(IXS), gsrc + i * gstride);
+      if (tid < R) cp_async<sizeof(T2)>(&s[tid * PS + pad(MX)], &src[(long long)MX * a.ny + tid]);  // Nyquist column
+    } else {
+      for (int e = tid; e < (MX + 1) * R; e += NTHREADS) {
+        int ix = e / R, r = e - ix * R;
+        cp_async<sizeof(T2)>(&s[r * PS + pad(ix)], &src[(long long)ix * a.ny + r]);
+      }
     }
     cp_async_wait_all();
     __syncthreads();
@@ -352,11 +397,12 @@ fused_row_kernel(RowArgs<T> a) {
   //   X[M-k] = 1/2 conj[(Z[k] + conj Z[M-k]) + i w_k (Z[k] - conj Z[M-k])]      (w_{M-k} = -conj w_k)
   // with Z[M] = Z[0]; k = 0 yields X[0] and the Nyquist column X[M]
   T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + iy0;
+#pragma unroll 4
   for (int e = tid; e < (MX / 2 + 1) * R; e += NTHREADS) {
     int k = e / R, r = e - k * R;
     const T2 *zr = s + r * PS;
     T2 zk = zr[pad(k)], zm = zr[pad(k == 0 ? 0 : MX - k)];
-    T2 w = a.tw[k * tws_n];
+    T2 w = ldg2(a.tw + k * tws_n);
     T2 sum = cadd(zk, cconj(zm)), dif = csub(zk, cconj(zm));
     T2 pw = mul_i<+1>(cmul(w, dif));
     T2 x0, x1;
@@ -414,7 +460,7 @@ struct BinStore {
 };
 
 template <typename T, int LY, int NC>
-__global__ void __launch_bounds__(NC *(LY / 16))
+__global__ void __launch_bounds__(NC *(LY / 16), (NC == 1 ? minb_for(LY / 16, OX_KC_REGS) : 1))
 fused_col_bin_kernel(ColBinArgs<T> a, double *__restrict__ partial /*[nbatch][gridDim.x][NS][nslots]*/) {
   typedef typename V2<T>::type T2;
   typedef BlockFFT<T, LY> FFT;
@@ -605,7 +651,7 @@ int launch_col_bin(ColBinArgs<T> &a, double *partial, int nbatch, int nblk) {
 template <typename T, int MX>
 struct RowCfg {
   typedef typename V2<T>::type T2;
-  static constexpr int WANT = sizeof(T2) == 16 ? 4 : 8;
+  static constexpr int WANT = sizeof(T2) == 16 ? OX_KB_ROWS64 : 8;
   static constexpr int R = (sizeof(T2) * WANT * padded_size(MX) <= 200 * 1024) ? WANT : WANT / 2;
 };
 
@@ -773,7 +819,7 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
   ca.tw_len = fs.tw_len;
   ca.ny = g->ny; ca.mx = g->nx / 2;
   ca.nslots = pl->b->nslots;
-  ca.cols_per_block = 8;
+  ca.cols_per_block = OX_KC_COLS;
   ca.rot = (flags & OX_FLAG_ROT) ? 1 : 0;
   ca.rot_sgn = sa.rot_sgn;
   int nblk = (g->nxh + ca.cols_per_block - 1) / ca.cols_per_block;

@@ -9,7 +9,7 @@
 //     memory: {-2/c_i, -2 ln c_i}); w = fma(m, -2/c_i, 2) = -2 (m/c_i - 1), |w| <= 2^-7;
 //     -2 ln u1 = (e-53)(-2 ln 2) + (-2 ln c_i) + sum_{k=1..6} w^k / (k 2^(k-1)).  c_0 = 1 and c_128 = 2
 //     keep the relative accuracy as u1 -> 1 (the constant terms cancel exactly).
-//   * sqrt: rsqrt.approx.f64 seed + two Goldschmidt steps + one correction.
+//   * sqrt: rsqrt.approx.f64 seed + one Goldschmidt step + one Newton correction.
 //   * e^{2 pi i u2}: the nearest quarter turn comes from the integer bits of b (no range reduction),
 //     the remainder |t| <= 1/8 turn goes through degree-6/7 polynomials in t^2 (tools/gen_rng_tables.py:
 //     fit errors 4e-17 / 2e-17).
@@ -76,15 +76,14 @@ __device__ __forceinline__ void box_muller_fast(uint4 x, const double2 *__restri
   p = fma(p, w, c_log[1]);
   p = fma(p, w, c_log[0]);
   double L = fma(ed, OX_RNG_NEG2LN2, t.y) + fma(p, w * w, w);
-  // ---- r = sqrt(L); L = 0 (u1 = 1, probability 2^-53) is lifted to 1e-300 so that rsqrt stays finite
-  L = fmax(L, 1e-300);
+  // ---- r = sqrt(L).  L = 0 (u1 = 1, probability 2^-53) becomes 1e-300 so that rsqrt stays finite; every
+  // other L (>= 2^-52) is unchanged by the addition.  rsqrt.approx seed (2^-22) -> one Goldschmidt step
+  // (2^-43) -> one Newton correction with the half-reciprocal h (full precision).
+  L += 1e-300;
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(L));
   double g = L * y, h = 0.5 * y;
-  double e = fma(-h, g, 0.5);
-  g = fma(g, e, g);
-  h = fma(h, e, h);
-  e = fma(-h, g, 0.5);
+  const double e = fma(-h, g, 0.5);
   g = fma(g, e, g);
   h = fma(h, e, h);
   g = fma(fma(-g, g, L), h, g);

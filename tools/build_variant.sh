@@ -1,0 +1,11 @@
+#!/bin/bash
+# Builds a tuning variant of liborphx.so: tools/build_variant.sh NAME -DOX_KB_ROWS64=2 ...
+# -> orphics_b200/_lib/liborphx_NAME.so (select with ORPHX_LIB=...); only ox_fused.cu is recompiled.
+set -e
+cd "$(dirname "$0")/../orphics_b200/csrc"
+name=$1; shift
+make -s >/dev/null
+nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -c ox_fused.cu -o build/ox_fused_$name.o
+objs=$(ls build/ox_*.o | grep -v "ox_fused" | tr '\n' ' ')
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../_lib/liborphx_$name.so $objs build/ox_fused_$name.o -L/usr/local/cuda/lib64 -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+echo built liborphx_$name.so

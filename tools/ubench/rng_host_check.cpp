@@ -26,13 +26,12 @@ static void bm(uint32_t xx, uint32_t xy, uint32_t xz, uint32_t xw, double &n1, d
   p = fma(p, w, c_log[2]); p = fma(p, w, c_log[1]); p = fma(p, w, c_log[0]);
   double L = fma(ed, OX_RNG_NEG2LN2, t1) + fma(p, w * w, w);
   Lout = L;
-  L = fmax(L, 1e-300);
+  L += 1e-300;
   double y = hilo(hiint((double)(1.0f / sqrtf((float)L))), 0);   // ~22-bit seed, low word zero
   if (L < 1e-30) y = hilo(hiint(1.0 / sqrt(L)), 0);
+  y *= (1.0 + 2.3e-7);                                            // worst-case seed error 2^-22
   double g = L * y, h = 0.5 * y;
-  double e = fma(-h, g, 0.5);
-  g = fma(g, e, g); h = fma(h, e, h);
-  e = fma(-h, g, 0.5);
+  const double e = fma(-h, g, 0.5);
   g = fma(g, e, g); h = fma(h, e, h);
   g = fma(fma(-g, g, L), h, g);
   const unsigned kb_hi = xz >> 11, kb_lo = (xw >> 11) | (xz << 21);
