@@ -196,6 +196,10 @@ int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int
  * count, for an in-place NCCL all-reduce (Statistics.add_stack / allreduce, stats.py:1134-1158,1227-1228) */
 int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem);
 int ox_qe_meanfield_reset(ox_qeplan *q);
+/* which implementation the plan runs: 0 = full-plane c2c chain on cuFFT (EB, unsymmetric filters),
+ * 1 = TT on half planes with cuFFT r2c/c2r, 2 = TT on half planes with the hand-written FFT passes
+ * (power-of-two maps; ORPHX_QE=cufft in the environment selects 1 instead) */
+int ox_qe_path(ox_qeplan *q);
 
 /* maps.filter_map (maps.py:1922-1923): Re(ifft(fft(m) * kfilter)) / Npix for nbatch x ncomp real maps;
  * kfilter is a real float64 full-plane [ny][nx] array (beam, l-mask, Wiener filter) */

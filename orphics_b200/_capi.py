@@ -103,6 +103,7 @@ SIGNATURES = {
     "ox_qe_reconstruct": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i],
     "ox_qe_meanfield": [_vp, _pvp, _pvp, _pll],
     "ox_qe_meanfield_reset": [_vp],
+    "ox_qe_path": [_vp],
     "ox_fft_c2c": [_vp, _vp, _i, _i, _i, _d, _vp, _i],
     "ox_power_filter": [_vp, _vp, _i, _i, _vp, _i, _vp, _i],
 }

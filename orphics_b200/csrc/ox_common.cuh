@@ -202,6 +202,8 @@ int sim_stage_inputs(ox_simplan *p, const long long *seeds_host, int nsim, int n
                      int noise_where, const double **noise_dev);
 // fused path (ox_fused.cu)
 bool fused_supported(int ny, int nx, int ncomp, int dtype);
+// twiddle table exp(-2 pi i j / len), j < len, in the plan dtype (long-double accurate)
+int fused_make_twiddles(int len, int dtype, DevBuf &buf);
 int fused_prepare(ox_simplan *s, ox_binner *b, FusedState &fs);
 int fused_run(ox_pipeline *pl, int nsim, int noise_mode, const double *noise_dev, int flags, bool keep_maps,
               cudaEvent_t *ev);

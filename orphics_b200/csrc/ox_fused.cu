@@ -25,17 +25,16 @@
 
 #include "ox_common.cuh"
 #include "ox_fft.cuh"
+#include "ox_fused_kernels.cuh"
 #include "ox_rng.cuh"
 
 using namespace ox;
 using namespace oxfft;
+using namespace oxk;
 
 // compile-time tuning knobs (defaults = the measured best on B200, profiles/r01_variants.txt)
 #ifndef OX_KA_REGS
 #define OX_KA_REGS 0   // register cap per thread asked of K_A (T-only), 0 = none
-#endif
-#ifndef OX_KB_ROWS64
-#define OX_KB_ROWS64 4  // rows per CTA of K_B for 16-byte elements (64 B segments)
 #endif
 #ifndef OX_KC_REGS
 #define OX_KC_REGS 128   // register cap per thread asked of K_C (T-only), 0 = none
@@ -60,19 +59,6 @@ __device__ __forceinline__ void rot_cs(double y, double x, double sgn, double &c
     s = sgn * (-2.0 * x * y) * inv;
   }
 }
-
-// asynchronous global -> shared copy of one element (LDGSTS): no register staging
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// load through the read-only (non-coherent) path: the compiler may reorder it across stores
-__device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
-__device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
 
 // deterministic in-warp reduce-by-key: afterwards the lowest lane of every group of equal keys
 // holds the group's sums (fixed shuffle tree, see ox_binner.cu)
@@ -107,19 +93,6 @@ struct SimColArgs {
   int ny, nx, mx;  // mx = nx/2
   int rot, cov_symmetric;
   double scale, rot_sgn;
-};
-
-template <typename T2>
-struct GlobalStore {
-  T2 *dst;
-  __device__ __forceinline__ void operator()(int f, T2 v, int) const { dst[f] = v; }
-};
-
-// first-stage input held in registers (m is a compile-time constant after unrolling)
-template <typename T2>
-struct RegLoad {
-  const T2 *v;
-  __device__ __forceinline__ T2 operator()(int, int m) const { return v[m]; }
 };
 
 // Hermitian part of the simulated Fourier field at pixel (iy, ix) of the half plane:
@@ -264,157 +237,6 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
   }
 }
 
-// ---- K_B -------------------------------------------------------------------------------
-template <typename T>
-struct RowArgs {
-  const typename V2<T>::type *Hin;  // transposed half plane [plane][mx+1][ny] or null
-  const T *map_in;                  // real maps [plane][ny][nx] (used when Hin == null)
-  typename V2<T>::type *Hout;       // transposed half plane out or null
-  T *map_out;                       // real maps out (before the window) or null
-  const T *window;                  // [ny][nx] or null
-  const typename V2<T>::type *tw;
-  int tw_len;
-  int ny, nx, mx;
-};
-
-// first-stage input of the c2r transform: Z[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/Nx} (X[k] - conj X[M-k])
-template <typename T2, int MX>
-struct PackLoad {
-  const T2 *row;  // X[0..MX] in padded shared memory
-  T2 wu;          // e^{+2 pi i u / Nx} of this thread
-  // k = u + m*NT and NT/Nx = 1/32, so e^{+2 pi i k/Nx} = wu * e^{2 pi i m/32}: the 16 factors are
-  // compile-time constants after unrolling (no table loads: the kernel is L1/shared-memory bound)
-  __device__ __forceinline__ T2 operator()(int k, int m) const {
-    constexpr double C32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
-                                0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785,
-                                0.0, -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474,
-                                -0.70710678118654752440, -0.83146961230254523708, -0.92387953251128675613, -0.98078528040323044913};
-    constexpr double S32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
-                                0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913,
-                                1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
-                                0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785};
-    T2 xk = row[pad(k)], xm = row[pad(MX - k)];
-    typedef decltype(xk.x) T;
-    T2 w;
-    w.x = wu.x * (T)C32[m] - wu.y * (T)S32[m];
-    w.y = wu.x * (T)S32[m] + wu.y * (T)C32[m];
-    T2 sum = cadd(xk, cconj(xm)), dif = csub(xk, cconj(xm));
-    return cadd(sum, mul_i<+1>(cmul(w, dif)));
-  }
-};
-
-// last-stage output of the c2r transform: z[n] = x[2n] + i x[2n+1]; store the map, apply the taper and
-// KEEP the element in registers: the outputs u + m*NT of a thread's last stage are exactly the inputs
-// of its first forward butterfly, so the real-space row never goes back to shared memory
-template <typename T>
-struct WindowKeep {
-  typedef typename V2<T>::type T2;
-  T2 *keep;          // registers [16]
-  T2 *map_row;       // global or null
-  const T2 *win_row; // global or null
-  __device__ __forceinline__ void operator()(int n, T2 z, int m) const {
-    if (map_row) map_row[n] = z;
-    if (win_row) {
-      T2 w = ldg2(win_row + n);  // read-only path: may be hoisted above the map stores of earlier elements
-      z.x *= w.x;
-      z.y *= w.y;
-    }
-    keep[m] = z;
-  }
-};
-
-// R rows per CTA, each a length-MX complex FFT handled by NT = MX/16 threads
-template <typename T, int MX, int R>
-__global__ void __launch_bounds__(R *(MX / 16), (R * (MX / 16) <= 256 ? 2 : 1))
-fused_row_kernel(RowArgs<T> a) {
-  typedef typename V2<T>::type T2;
-  typedef BlockFFT<T, MX> FFT;
-  constexpr int NT = FFT::NT, NTHREADS = R * NT, PS = padded_size(MX), NX = 2 * MX;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T2 *s = reinterpret_cast<T2 *>(smem_raw);  // [R][PS]
-  const int tid = threadIdx.x;
-  const int iy0 = blockIdx.x * R;
-  const long long plane = blockIdx.y;
-  const int f = tid / NT, u = tid - f * NT;
-  T2 *row = s + f * PS;
-  const int tws_n = a.tw_len / NX;  // stride for exp(-2 pi i k / Nx)
-  typename FFT::Twiddles tws;
-  tws.init(a.tw, a.tw_len / MX, u);
-  // the NT threads of one row synchronise among themselves only (named barriers need whole warps)
-  const int bar = (NT % 32 == 0) ? 1 + f : 0;
-  const long long rowoff = (long long)(iy0 + f) * MX;
-  T2 keep[16];
-  WindowKeep<T> wst;
-  wst.keep = keep;
-  wst.map_row = a.map_out ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
-  wst.win_row = a.window ? reinterpret_cast<const T2 *>(a.window) + rowoff : nullptr;
-  if (a.Hin) {
-    // tile load: for each ix the R rows are R*16 B contiguous in the transposed layout
-    const T2 *src = a.Hin + plane * (long long)(MX + 1) * a.ny + iy0;
-    // (unrolled with constant strides: a loop that bumps the address registers stalls every
-    // iteration on the write-after-read scoreboard of the previous LDGSTS)
-    if constexpr ((NTHREADS / R) % 16 == 0 && (MX * R) % NTHREADS == 0) {
-      constexpr int IXS = NTHREADS / R;  // ix advance per iteration; pad(ix + IXS) = pad(ix) + pad(IXS)
-      const int ix0 = tid / R, r = tid - ix0 * R;
-      T2 *sdst = &s[r * PS + pad(ix0)];
-      const T2 *gsrc = &src[(long long)ix0 * a.ny + r];
-      const long long gstride = (long long)IXS * a.ny;
-#pragma unroll
-      for (int i = 0; i < MX * R / NTHREADS; i++) cp_async<sizeof(T2)>(sdst + i * pad(IXS), gsrc + i * gstride);
-      if (tid < R) cp_async<sizeof(T2)>(&s[tid * PS + pad(MX)], &src[(long long)MX * a.ny + tid]);  // Nyquist column
-    } else {
-      for (int e = tid; e < (MX + 1) * R; e += NTHREADS) {
-        int ix = e / R, r = e - ix * R;
-        cp_async<sizeof(T2)>(&s[r * PS + pad(ix)], &src[(long long)ix * a.ny + r]);
-      }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    T2 wu = a.tw[u * tws_n];
-    wu.y = -wu.y;  // e^{+2 pi i u/Nx}
-    PackLoad<T2, MX> ld{row, wu};
-    FFT::template run<+1, true, false>(row, tws, u, bar, ld, wst);
-  } else {
-    // real map rows viewed as z[n] = x[2n] + i x[2n+1]
-    const T2 *src = reinterpret_cast<const T2 *>(a.map_in + (plane * a.ny + iy0 + f) * (long long)NX);
-#pragma unroll
-    for (int m = 0; m < 16; m++) {
-      const int n = u + m * NT;
-      wst(n, src[n], m);
-    }
-  }
-  if (!a.Hout) return;
-  {
-    // forward transform fed from registers; IN_SMEM = true: the other threads of the row may still be
-    // reading the inverse transform's last exchange, so the first stage synchronises before it writes
-    RegLoad<T2> ld{keep};
-    SmemStore<T2> st{row};
-    FFT::template run<-1, true, true>(row, tws, u, bar, ld, st);
-  }
-  __syncthreads();
-  // transposed store with the r2c unpacking fused in, two outputs per pair (k, M-k) of inputs:
-  //   X[k]   = 1/2 [(Z[k] + conj Z[M-k]) - i w_k (Z[k] - conj Z[M-k])],  w_k = e^{-2 pi i k/Nx}
-  //   X[M-k] = 1/2 conj[(Z[k] + conj Z[M-k]) + i w_k (Z[k] - conj Z[M-k])]      (w_{M-k} = -conj w_k)
-  // with Z[M] = Z[0]; k = 0 yields X[0] and the Nyquist column X[M]
-  T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + iy0;
-#pragma unroll 4
-  for (int e = tid; e < (MX / 2 + 1) * R; e += NTHREADS) {
-    int k = e / R, r = e - k * R;
-    const T2 *zr = s + r * PS;
-    T2 zk = zr[pad(k)], zm = zr[pad(k == 0 ? 0 : MX - k)];
-    T2 w = ldg2(a.tw + k * tws_n);
-    T2 sum = cadd(zk, cconj(zm)), dif = csub(zk, cconj(zm));
-    T2 pw = mul_i<+1>(cmul(w, dif));
-    T2 x0, x1;
-    x0.x = (T)0.5 * (sum.x - pw.x);
-    x0.y = (T)0.5 * (sum.y - pw.y);
-    x1.x = (T)0.5 * (sum.x + pw.x);
-    x1.y = -(T)0.5 * (sum.y + pw.y);
-    dst[(long long)k * a.ny + r] = x0;
-    if (2 * k != MX) dst[(long long)(MX - k) * a.ny + r] = x1;
-  }
-}
-
 // ---- K_C -------------------------------------------------------------------------------
 template <typename T>
 struct ColBinArgs {
@@ -425,12 +247,6 @@ struct ColBinArgs {
   int tw_len;
   int ny, mx, nslots, cols_per_block, rot;
   double rot_sgn;
-};
-
-template <typename T2>
-struct GlobalLoad {
-  const T2 *src;
-  __device__ __forceinline__ T2 operator()(int e, int) const { return src[e]; }
 };
 
 // last stage of the T-only column transform: |k|^2 x Hermitian weight straight into the
@@ -601,14 +417,6 @@ __global__ void bandpower_finalize2_kernel(const double *__restrict__ partial, i
   if (lane == 0) bp[(size_t)m * ns * nbins + gw] = (acc * normfact) / count[bin + 1];
 }
 
-template <typename F>
-int set_smem(F kernel, size_t bytes) {
-  if (bytes > 48 * 1024) OX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return OX_OK;
-}
-
-constexpr size_t SMEM_MAX = 227 * 1024;
-
 template <typename T, int LY, int NC, int MODE>
 int launch_sim_col_mode(SimColArgs<T> &a, void *Ht, int nsim) {
   typedef typename V2<T>::type T2;
@@ -643,29 +451,6 @@ int launch_col_bin(ColBinArgs<T> &a, double *partial, int nbatch, int nblk) {
   OX_TRY(set_smem(k, smem));
   dim3 grid(nblk, nbatch);
   k<<<grid, NTHREADS, smem, g_stream>>>(a, partial);
-  OX_KERNEL_CHECK();
-  return OX_OK;
-}
-
-// rows per CTA: 64-byte segments where shared memory allows (4 x double2 / 8 x float2)
-template <typename T, int MX>
-struct RowCfg {
-  typedef typename V2<T>::type T2;
-  static constexpr int WANT = sizeof(T2) == 16 ? OX_KB_ROWS64 : 8;
-  static constexpr int R = (sizeof(T2) * WANT * padded_size(MX) <= 200 * 1024) ? WANT : WANT / 2;
-};
-
-template <typename T, int MX>
-int launch_row(RowArgs<T> &a, long long nplanes) {
-  typedef typename V2<T>::type T2;
-  constexpr int R = RowCfg<T, MX>::R;
-  size_t smem = sizeof(T2) * R * padded_size(MX);
-  OX_REQUIRE(smem <= SMEM_MAX, "fused row: %d rows of %d need %zu B of shared memory", R, MX, smem);
-  OX_REQUIRE(a.ny % R == 0, "ny must be a multiple of %d", R);
-  auto k = fused_row_kernel<T, MX, R>;
-  OX_TRY(set_smem(k, smem));
-  dim3 grid(a.ny / R, (unsigned)nplanes);
-  k<<<grid, R * (MX / 16), smem, g_stream>>>(a);
   OX_KERNEL_CHECK();
   return OX_OK;
 }
@@ -796,16 +581,9 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
   ra.tw = fs.tw.as<T2>();
   ra.tw_len = fs.tw_len;
   ra.ny = g->ny; ra.nx = g->nx; ra.mx = g->nx / 2;
-  st = OX_ERR_UNSUPPORTED;
-  switch (g->nx / 2) {
-    case 128: st = launch_row<T, 128>(ra, (long long)nsim * nc); break;
-    case 256: st = launch_row<T, 256>(ra, (long long)nsim * nc); break;
-    case 512: st = launch_row<T, 512>(ra, (long long)nsim * nc); break;
-    case 1024: st = launch_row<T, 1024>(ra, (long long)nsim * nc); break;
-    case 2048: st = launch_row<T, 2048>(ra, (long long)nsim * nc); break;
-    case 4096: st = launch_row<T, 4096>(ra, (long long)nsim * nc); break;
-    default: set_error("fused path: unsupported nx=%d", g->nx);
-  }
+  ra.map_in_group_stride = (long long)g->ny * g->nx;
+  typedef RowModes<ROW_IN_H | ROW_OUT_H> PipelineRowModes;
+  st = launch_row_any<T>(ra, (long long)nsim * nc, PipelineRowModes());
   OX_TRY(st);
   OX_MARK(2);
   OX_MARK(3);

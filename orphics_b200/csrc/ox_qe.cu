@@ -13,8 +13,10 @@
 // legs (1 read, 3 writes), real-space products (3 reads, 2 writes), divergence x normalisation
 // (2 reads, 1 write, + the mean-field accumulator).
 #include <math.h>
+#include <stdlib.h>
 
 #include "ox_common.cuh"
+#include "ox_fused_kernels.cuh"
 
 using namespace ox;
 
@@ -29,6 +31,12 @@ struct ox_qeplan {
   DevBuf legs, fields, prod, pk, khat, full, out_real;
   DevBuf mf;               // double2 [ny][nxh] mean-field accumulator of kappa_hat(l)
   DevBuf mf_count;         // int64
+  // hand-written FFT path (TT on half planes, power-of-two maps): tables and intermediates in the
+  // transposed half-plane layout [plane][ix][iy] of ox_fused_kernels.cuh
+  bool fused = false;
+  int tw_len = 0;
+  DevBuf tw, wxyT, wyT, normT, legT;
+  DevBuf Hx, Hy, Kx, Ky, Lt, Pt, khT;
 };
 
 namespace {
@@ -227,6 +235,314 @@ __global__ void table_half_kernel(const T *__restrict__ full, int ny, int nx, in
   half[i] = full[(long long)iy * nx + ix];
 }
 
+// ---- TT on the hand-written FFT engine -------------------------------------------------------
+// Same arithmetic as the three kernels above, attached to the 1-D FFT passes as load/store functors:
+//   Q1 rows   : r2c of the input maps                      -> transposed half plane      (fused_row_kernel)
+//   Q2a cols  : forward FFT along y                         -> k(l)                       (ColPlainOps)
+//   Q2b cols  : k x {i lx W_XY, i ly W_XY, W_Y}/N -> inverse FFT along y, three legs      (LegsOps)
+//   Q3a rows  : c2r of the three legs                       -> real fields
+//   Q3b rows  : (gradient leg x third field) -> r2c, two products (the "window" of the row kernel)
+//   Q4  cols  : forward FFT along y of P_x, then of P_y; the store functors form
+//               kappa_hat = -A_L (i lx P_x + i ly P_y) in the transposed layout           (DivOps)
+//   finish    : tiled transposition to the natural layout (full plane for returnFt) + mean field
+template <typename T>
+struct ColPlainOps {
+  typedef typename oxfft::V2<T>::type T2;
+  const T2 *src;
+  T2 *dst;
+  int ny, nxh;
+  double scale;
+  struct Load {
+    const T2 *p;
+    double sc;
+    __device__ __forceinline__ T2 operator()(int e, int) const {
+      T2 z = p[e];
+      return mk<T2>((double)z.x * sc, (double)z.y * sc);
+    }
+  };
+  typedef oxk::GlobalStore<T2> Store;
+  __device__ __forceinline__ Load load(int ix, int plane) const { return Load{src + ((size_t)plane * nxh + ix) * ny, scale}; }
+  __device__ __forceinline__ Store store(int ix, int plane) const { return Store{dst + ((size_t)plane * nxh + ix) * ny}; }
+};
+
+template <typename T>
+struct LegsOps {
+  typedef typename oxfft::V2<T>::type T2;
+  const T2 *kx, *ky;   // [nb][nxh][ny]
+  const T *legT;       // [3][nxh][ny]: W_XY/N, ly W_XY/N, W_Y/N (precombined at plan creation: one table
+                       // value per element keeps all 16 loads of a thread in flight)
+  const double *lx;
+  T2 *Lt;              // [nb][3][nxh][ny]
+  int ny, nxh, nb;
+  // leg factor (alpha + i beta) W: (0, lx) / (0, 1) with the ly-weighted table / (1, 0); no branch on the
+  // leg inside the element loop, so that the 32 loads of a thread are all issued before the first use
+  struct Load {
+    const T2 *k;
+    const T *w;
+    double alpha, beta;
+    __device__ __forceinline__ T2 operator()(int e, int) const {
+      const T2 z = k[e];
+      const double wg = (double)__ldg(w + e);
+      return mk<T2>(wg * (alpha * (double)z.x - beta * (double)z.y), wg * (alpha * (double)z.y + beta * (double)z.x));
+    }
+  };
+  typedef oxk::GlobalStore<T2> Store;
+  // plane = leg * nb + m: the realisations of one leg share its table column, the legs of one
+  // realisation share its k column
+  __device__ __forceinline__ Load load(int ix, int plane) const {
+    const int leg = plane / nb, m = plane - leg * nb;
+    const size_t col = ((size_t)m * nxh + ix) * ny;
+    return Load{(leg == 2 ? ky : kx) + col, legT + ((size_t)leg * nxh + ix) * ny, leg == 2 ? 1.0 : 0.0,
+                leg == 0 ? lx[ix] : (leg == 1 ? 1.0 : 0.0)};
+  }
+  __device__ __forceinline__ Store store(int ix, int plane) const {
+    const int leg = plane / nb, m = plane - leg * nb;
+    return Store{Lt + (((size_t)m * 3 + leg) * nxh + ix) * ny};
+  }
+};
+
+// legT[0] = W_XY/N, legT[1] = ly W_XY/N, legT[2] = W_Y/N in the transposed layout
+template <typename T>
+__global__ void leg_tables_kernel(const T *__restrict__ wxyT, const T *__restrict__ wyT, const double *__restrict__ ly, int ny,
+                                  int nxh, double invn, T *__restrict__ legT) {
+  const long long nh = (long long)ny * nxh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nh; i += (long long)gridDim.x * blockDim.x) {
+    const int iy = (int)(i % ny);
+    const double wg = (double)wxyT[i] * invn;
+    legT[i] = (T)wg;
+    legT[nh + i] = (T)(ly[iy] * wg);
+    legT[2 * nh + i] = (T)((double)wyT[i] * invn);
+  }
+}
+
+// kappa_hat in the transposed layout (input of the inverse transform to the kappa map):
+// khT[m][ix][iy] = -A (i lx P_x + i ly P_y), same arithmetic as qe_tt_div_kernel
+template <typename T, typename T2>
+__global__ void qe_divT_kernel(const T2 *__restrict__ Pk, const T *__restrict__ normT, const double *__restrict__ ly,
+                               const double *__restrict__ lx, int ny, int nx, int nxh, double scale, T2 *__restrict__ khT) {
+  const long long nh = (long long)ny * nxh;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const long long m = blockIdx.y;
+  const int ix = (int)(i / ny), iy = (int)(i - (long long)ix * ny);
+  const double x = (2 * ix == nx) ? 0.0 : lx[ix], y = (2 * iy == ny) ? 0.0 : ly[iy], a = -(double)normT[i];
+  const T2 px = Pk[m * 2 * nh + i], py = Pk[(m * 2 + 1) * nh + i];
+  const double fr = -(x * (double)px.y + y * (double)py.y), fi = x * (double)px.x + y * (double)py.x;
+  khT[m * nh + i] = mk<T2>(a * fr * scale, a * fi * scale);
+}
+
+// out[ix][iy] = in[iy][ix] for the nxh half-plane columns of a [ny][ldin] array (tables, alreadyFTed k-maps)
+template <typename V>
+__global__ void to_halfT_kernel(const V *__restrict__ in, int ny, int ldin, int nxh, long long in_plane, V *__restrict__ out) {
+  __shared__ V tile[32][33];
+  const long long m = blockIdx.z;
+  const int ix0 = blockIdx.x * 32, iy0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int iy = iy0 + j, ix = ix0 + threadIdx.x;
+    if (iy < ny && ix < nxh) tile[j][threadIdx.x] = in[m * in_plane + (long long)iy * ldin + ix];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int ix = ix0 + j, iy = iy0 + threadIdx.x;
+    if (iy < ny && ix < nxh) out[(m * nxh + ix) * ny + iy] = tile[threadIdx.x][j];
+  }
+}
+
+// kappa_hat(l) = -A (i lx P_x + i ly P_y) (arithmetic of qe_tt_div_kernel) from the transposed products
+// Pk[m][2][ix][iy], written in the natural layout: full[m] (full plane, Hermitian extension; returnFt)
+// and the mean-field accumulator mf[iy][ix] += sum_m kappa_hat (fixed m order)
+template <typename T, typename T2>
+__global__ void qe_finish_kernel(const T2 *__restrict__ Pk, const T *__restrict__ norm, const double *__restrict__ ly,
+                                 const double *__restrict__ lx, int ny, int nx, int nxh, int nb, T2 *__restrict__ full,
+                                 double2 *__restrict__ mf) {
+  __shared__ T2 tile[2][32][33];
+  const int ix0 = blockIdx.x * 32, iy0 = blockIdx.y * 32;
+  const long long n = (long long)ny * nx, nh = (long long)ny * nxh;
+  const int ixo = ix0 + threadIdx.x;   // this thread's output column
+  const double x = (ixo < nxh && 2 * ixo != nx) ? lx[ixo] : 0.0;
+  double2 acc[4];
+  double a[4], y[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; jj++) {
+    const int iy = iy0 + threadIdx.y + 8 * jj;
+    acc[jj] = make_double2(0.0, 0.0);
+    a[jj] = ixo < nxh ? -(double)norm[(long long)iy * nxh + ixo] : 0.0;
+    y[jj] = (2 * iy == ny) ? 0.0 : ly[iy];
+  }
+  for (int m = 0; m < nb; m++) {
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const int ix = ix0 + j, iy = iy0 + threadIdx.x;
+      if (ix < nxh) {
+        tile[0][j][threadIdx.x] = Pk[((long long)m * 2 * nxh + ix) * ny + iy];
+        tile[1][j][threadIdx.x] = Pk[(((long long)m * 2 + 1) * nxh + ix) * ny + iy];
+      }
+    }
+    __syncthreads();
+    if (ixo >= nxh) continue;
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = threadIdx.y + 8 * jj, iy = iy0 + j;
+      const T2 px = tile[0][threadIdx.x][j], py = tile[1][threadIdx.x][j];
+      const double fr = -(x * (double)px.y + y[jj] * (double)py.y), fi = x * (double)px.x + y[jj] * (double)py.x;
+      const double kr = a[jj] * fr, ki = a[jj] * fi;
+      acc[jj].x += kr;
+      acc[jj].y += ki;
+      if (full) {
+        full[m * n + (long long)iy * nx + ixo] = mk<T2>(kr, ki);
+        if (ixo > 0 && 2 * ixo < nx) {
+          const int my = iy ? ny - iy : 0;
+          full[m * n + (long long)my * nx + (nx - ixo)] = mk<T2>(kr, -ki);
+        }
+      }
+    }
+  }
+  if (mf && ixo < nxh) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const long long o = (long long)(iy0 + threadIdx.y + 8 * jj) * nxh + ixo;
+      double2 v = mf[o];
+      v.x += acc[jj].x;
+      v.y += acc[jj].y;
+      mf[o] = v;
+    }
+  }
+}
+
+// row passes of the estimator: r2c of maps, c2r to maps, product with a second map -> r2c
+typedef oxk::RowModes<oxk::ROW_OUT_H, oxk::ROW_IN_H | oxk::ROW_OUT_MAP, oxk::ROW_WIN | oxk::ROW_OUT_H> QeRowModes;
+
+bool qe_fused_supported(int ny, int nx) {
+  auto p2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  return p2(ny) && p2(nx) && ny >= 512 && ny <= 8192 && nx >= 256 && nx <= 8192;
+}
+
+template <typename T, typename T2>
+int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, int nb, int already_ft, int return_ft,
+                        int accumulate, void *out, int out_where) {
+  ox_geometry *g = q->g;
+  const int ny = g->ny, nx = g->nx, nxh = g->nxh;
+  const long long n = (long long)ny * nx, nh = (long long)ny * nxh;
+  const double invn = 1.0 / ((double)ny * (double)nx);
+  const double *ly = g->ly.as<double>(), *lx = g->lx.as<double>();
+  const bool two = (y != nullptr && y != x);
+  const size_t hb = sizeof(T2) * (size_t)q->max_batch * nh;
+  OX_TRY(q->Kx.ensure(hb));
+  if (two) OX_TRY(q->Ky.ensure(hb));
+  const dim3 tb(32, 8);
+  int st;
+  // ---- inputs -> k(l) in the transposed half-plane layout
+  for (int leg = 0; leg < (two ? 2 : 1); leg++) {
+    const void *src = leg ? y : x;
+    T2 *K = leg ? q->Ky.as<T2>() : q->Kx.as<T2>();
+    if (already_ft) {
+      const void *dsrc;
+      OX_TRY(stage_in(src, where, sizeof(T2) * (size_t)nb * n, q->full, &dsrc));
+      dim3 grid((nxh + 31) / 32, (ny + 31) / 32, nb);
+      to_halfT_kernel<T2><<<grid, tb, 0, g_stream>>>((const T2 *)dsrc, ny, nx, nxh, n, K);
+      OX_KERNEL_CHECK();
+    } else {
+      const void *dsrc = src;
+      if (where == OX_HOST) {
+        OX_TRY(q->in_real.ensure(sizeof(T) * (size_t)q->max_batch * n));
+        OX_CUDA(cudaMemcpyAsync(q->in_real.p, src, sizeof(T) * (size_t)nb * n, cudaMemcpyHostToDevice, g_stream));
+        dsrc = q->in_real.p;
+      }
+      OX_TRY(q->Hx.ensure(hb));
+      oxk::RowArgs<T> ra;
+      ra.Hin = nullptr;
+      ra.map_in = (const T *)dsrc;
+      ra.Hout = q->Hx.as<T2>();
+      ra.map_out = nullptr;
+      ra.window = nullptr;
+      ra.tw = q->tw.as<T2>();
+      ra.tw_len = q->tw_len;
+      ra.ny = ny; ra.nx = nx; ra.mx = nx / 2;
+      ra.map_in_group_stride = n;
+      OX_TRY(oxk::launch_row_any<T>(ra, nb, QeRowModes()));                                            // Q1
+      ColPlainOps<T> op{q->Hx.as<T2>(), K, ny, nxh, 1.0};
+      OX_COL_DISPATCH(T, -1, op, q->tw.p, q->tw_len, nxh, nb, ny, st);                   // Q2a
+      OX_TRY(st);
+    }
+  }
+  // ---- legs -> real fields -> products
+  OX_TRY(q->Lt.ensure(3 * hb));
+  OX_TRY(q->fields.ensure(sizeof(T) * (size_t)q->max_batch * 3 * n));
+  OX_TRY(q->Pt.ensure(2 * hb));
+  {
+    LegsOps<T> op{q->Kx.as<T2>(), two ? q->Ky.as<T2>() : q->Kx.as<T2>(), q->legT.as<T>(), lx, q->Lt.as<T2>(), ny, nxh, nb};
+    OX_COL_DISPATCH(T, +1, op, q->tw.p, q->tw_len, nxh, 3LL * nb, ny, st);               // Q2b
+    OX_TRY(st);
+  }
+  {
+    oxk::RowArgs<T> ra;
+    ra.Hin = q->Lt.as<T2>();
+    ra.map_in = nullptr;
+    ra.Hout = nullptr;
+    ra.map_out = q->fields.as<T>();
+    ra.window = nullptr;
+    ra.tw = q->tw.as<T2>();
+    ra.tw_len = q->tw_len;
+    ra.ny = ny; ra.nx = nx; ra.mx = nx / 2;
+    OX_TRY(oxk::launch_row_any<T>(ra, 3LL * nb, QeRowModes()));                                        // Q3a
+    ra.Hin = nullptr;
+    ra.map_in = q->fields.as<T>();
+    ra.map_out = nullptr;
+    ra.Hout = q->Pt.as<T2>();
+    ra.window = q->fields.as<T>() + 2 * n;   // the third field of each realisation
+    ra.group = 2;
+    ra.map_in_group_stride = 3 * n;
+    ra.win_group_stride = 3 * n;
+    OX_TRY(oxk::launch_row_any<T>(ra, 2LL * nb, QeRowModes()));                                        // Q3b
+  }
+  {
+    ColPlainOps<T> op{q->Pt.as<T2>(), q->Pt.as<T2>(), ny, nxh, 1.0};   // in place: a CTA owns its column
+    OX_COL_DISPATCH(T, -1, op, q->tw.p, q->tw_len, nxh, 2LL * nb, ny, st);               // Q4
+    OX_TRY(st);
+  }
+  // ---- outputs
+  double2 *mf = accumulate ? q->mf.as<double2>() : nullptr;
+  const dim3 fgrid((nxh + 31) / 32, ny / 32);
+  if (return_ft || mf) {
+    T2 *fullp = nullptr;
+    if (return_ft) {
+      fullp = (T2 *)out;
+      if (out_where == OX_HOST) {
+        OX_TRY(q->full.ensure(sizeof(T2) * (size_t)nb * n));
+        fullp = q->full.as<T2>();
+      }
+    }
+    qe_finish_kernel<T, T2><<<fgrid, tb, 0, g_stream>>>(q->Pt.as<T2>(), q->norm.as<T>(), ly, lx, ny, nx, nxh, nb, fullp, mf);
+    OX_KERNEL_CHECK();
+    if (return_ft) {
+      if (out_where == OX_HOST) OX_TRY(stage_out(out, OX_HOST, fullp, sizeof(T2) * (size_t)nb * n));
+      return OX_OK;
+    }
+  }
+  // real-space kappa = IFFT(kappa_hat)/N: kappa_hat/N in the transposed layout, inverse FFT along y, c2r rows
+  OX_TRY(q->khT.ensure(hb));
+  OX_TRY(q->out_real.ensure(sizeof(T) * (size_t)q->max_batch * n));
+  {
+    dim3 gh((unsigned)((nh + QT - 1) / QT), nb);
+    qe_divT_kernel<T, T2><<<gh, QT, 0, g_stream>>>(q->Pt.as<T2>(), q->normT.as<T>(), ly, lx, ny, nx, nxh, invn, q->khT.as<T2>());
+    OX_KERNEL_CHECK();
+    ColPlainOps<T> op{q->khT.as<T2>(), q->khT.as<T2>(), ny, nxh, 1.0};
+    OX_COL_DISPATCH(T, +1, op, q->tw.p, q->tw_len, nxh, nb, ny, st);
+    OX_TRY(st);
+    oxk::RowArgs<T> ra;
+    ra.Hin = q->khT.as<T2>();
+    ra.map_in = nullptr;
+    ra.Hout = nullptr;
+    ra.map_out = q->out_real.as<T>();
+    ra.window = nullptr;
+    ra.tw = q->tw.as<T2>();
+    ra.tw_len = q->tw_len;
+    ra.ny = ny; ra.nx = nx; ra.mx = nx / 2;
+    OX_TRY(oxk::launch_row_any<T>(ra, nb, QeRowModes()));
+  }
+  return stage_out(out, out_where, q->out_real.p, sizeof(T) * (size_t)nb * n);
+}
+
 template <typename T, typename T2>
 int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb, int already_ft, int return_ft,
                   int accumulate, void *out, int out_where) {
@@ -235,6 +551,7 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
   const long long n = (long long)ny * nx, nh = (long long)ny * nxh;
   const double invn = 1.0 / ((double)ny * (double)nx);
   const double *ly = g->ly.as<double>(), *lx = g->lx.as<double>();
+  if (q->fused) return reconstruct_fused_T<T, T2>(q, x, y, where, nb, already_ft, return_ft, accumulate, out, out_where);
   const bool two = (y != nullptr && y != x);
   const long long plane = q->real_path ? nh : n;  // complex elements per staged k-map
   OX_TRY(q->kx.ensure(sizeof(T2) * (size_t)q->max_batch * plane));
@@ -352,6 +669,13 @@ int upload_tables(ox_qeplan *q, const double *wxy, const double *wy, const doubl
     OX_TRY(stage_in(src[t], where, sizeof(double) * n, stage, &d));
     OX_TRY(fullT.ensure(sizeof(T) * n));
     OX_TRY(cast_from_f64((const double *)d, fullT.p, n, q->dtype));
+    if (q->fused) {
+      DevBuf *dstT[3] = {&q->wxyT, &q->wyT, &q->normT};
+      OX_TRY(dstT[t]->ensure(sizeof(T) * nh));
+      dim3 grid((g->nxh + 31) / 32, (g->ny + 31) / 32, 1);
+      to_halfT_kernel<T><<<grid, dim3(32, 8), 0, g_stream>>>(fullT.as<T>(), g->ny, g->nx, g->nxh, n, dstT[t]->as<T>());
+      OX_KERNEL_CHECK();
+    }
     if (q->real_path) {
       OX_TRY(dst[t]->ensure(sizeof(T) * nh));
       table_half_kernel<T><<<(unsigned)((nh + QT - 1) / QT), QT, 0, g_stream>>>(fullT.as<T>(), g->ny, g->nx, g->nxh, dst[t]->as<T>());
@@ -362,6 +686,20 @@ int upload_tables(ox_qeplan *q, const double *wxy, const double *wy, const doubl
     }
     OX_CUDA(cudaStreamSynchronize(g_stream));
   }
+  return OX_OK;
+}
+
+template <typename T>
+int make_leg_tables(ox_qeplan *q) {
+  ox_geometry *g = q->g;
+  const long long nh = (long long)g->ny * g->nxh;
+  OX_TRY(q->legT.ensure(sizeof(T) * 3 * nh));
+  leg_tables_kernel<T><<<sm_count() * 8, QT, 0, g_stream>>>(q->wxyT.as<T>(), q->wyT.as<T>(), g->ly.as<double>(), g->ny, g->nxh,
+                                                            1.0 / ((double)g->ny * (double)g->nx), q->legT.as<T>());
+  OX_KERNEL_CHECK();
+  OX_CUDA(cudaStreamSynchronize(g_stream));
+  q->wxyT.release();
+  q->wyT.release();
   return OX_OK;
 }
 
@@ -385,7 +723,19 @@ int ox_qeplan_create(ox_geometry *g, int est, const double *wxy, const double *w
   q->fft.ny = g->ny;
   q->fft.nx = g->nx;
   q->fft.dtype = dtype;
+  // hand-written FFT path for TT on half planes (ORPHX_QE=cufft keeps the cuFFT chain)
+  const char *env = getenv("ORPHX_QE");
+  q->fused = q->real_path && qe_fused_supported(g->ny, g->nx) && !(env && !strcmp(env, "cufft"));
+  if (q->fused) {
+    q->tw_len = g->ny > g->nx ? g->ny : g->nx;
+    int ts = fused_make_twiddles(q->tw_len, dtype, q->tw);
+    if (ts != OX_OK) {
+      delete q;
+      return ts;
+    }
+  }
   int st = dtype == OX_F64 ? upload_tables<double>(q, wxy, wy, norm, where) : upload_tables<float>(q, wxy, wy, norm, where);
+  if (st == OX_OK && q->fused) st = dtype == OX_F64 ? make_leg_tables<double>(q) : make_leg_tables<float>(q);
   if (st == OX_OK) st = q->mf.ensure(sizeof(double2) * (size_t)g->ny * g->nxh);
   if (st == OX_OK) st = q->mf_count.ensure(sizeof(long long));
   if (st != OX_OK) {
@@ -407,6 +757,8 @@ int ox_qe_meanfield_reset(ox_qeplan *q) {
   OX_CUDA(cudaMemsetAsync(q->mf_count.p, 0, sizeof(long long), g_stream));
   return OX_OK;
 }
+
+int ox_qe_path(ox_qeplan *q) { return q ? (q->fused ? 2 : (q->real_path ? 1 : 0)) : -1; }
 
 int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem) {
   OX_REQUIRE(q, "null plan");

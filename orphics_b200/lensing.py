@@ -158,6 +158,13 @@ class qest(object):
                                    self.max_batch, int(real_path), C.byref(h)))
         self._plans[XY] = (h, real_path)
 
+    def path(self, XY):
+        """Implementation behind estimator XY: 'c2c' (full-plane chain on cuFFT), 'half' (TT on half
+        planes, cuFFT) or 'fused' (TT on half planes, hand-written FFT passes; include/orphx.h ox_qe_path)."""
+        if XY not in self._plans:
+            self._make_plan(XY)
+        return {0: 'c2c', 1: 'half', 2: 'fused'}[lib.ox_qe_path(self._plans[XY][0])]
+
     def _run(self, XY, X, Y, alreadyFTed, returnFt, accumulate):
         if XY not in self._plans:
             if XY in ('TT', 'EB'):

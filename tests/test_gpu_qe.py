@@ -41,9 +41,10 @@ def test_filters_and_normalisation_match_oracle(masked, theory):
     assert q._plans["TT"][1] == masked        # half-plane path only when the filters vanish at Nyquist
 
 
-@pytest.mark.parametrize("masked", [True, False])
-def test_tt_kappa_matches_oracle(masked, theory):
-    shape, wcs, so, wo, q, qo = setup(128, 2.0, theory, masked)
+@pytest.mark.parametrize("masked,npix,path", [(True, 128, "half"), (False, 128, "c2c"), (True, 512, "fused")])
+def test_tt_kappa_matches_oracle(masked, npix, path, theory):
+    shape, wcs, so, wo, q, qo = setup(npix, 2.0, theory, masked)
+    assert q.path("TT") == path
     qo.N.AL["TT"] = np.asarray(q.N.AL["TT"])          # identical set-up input: compare the per-map chain only
     rng = np.random.RandomState(3)
     T = rng.standard_normal(shape) * 50
@@ -93,13 +94,44 @@ def test_eb_kappa_matches_oracle(theory):
     assert relerr(q.kappa_from_map("EB", None, E, B), qo.kappa_from_map("EB", None, E, B)) < TOL64     # real E/B maps in
 
 
-def test_fp32_mode(theory):
+def test_tt_fused_equals_cufft_rectangular(theory, monkeypatch):
+    """Size-independent check at a size the oracle does not reach: the hand-written FFT passes and the
+    cuFFT chain are two implementations of the same estimator (1024 x 2048, batch, mean field)."""
+    from orphics_b200 import maps, lensing, cosmology
+    ny, nx, res = 1024, 2048, 1.0
+    shape, wcs = maps.rect_geometry(width_arcmin=nx * res, px_res_arcmin=res, height_arcmin=ny * res)
+    assert tuple(shape) == (ny, nx)
+    modl = maps.Geometry.get(shape, wcs).modlmap()
+    kw = dict(noise2d=np.zeros(shape) + (1.0 * np.pi / 180 / 60) ** 2, beam2d=maps.gauss_beam(modl, 1.5),
+              kmask=maps.mask_kspace(shape, wcs, lmin=300, lmax=2000), kmask_K=maps.mask_kspace(shape, wcs, lmin=20, lmax=3500),
+              unlensed_equals_lensed=True, max_batch=2)
+    qf = lensing.qest(shape, wcs, cosmology.default_theory(), **kw)
+    assert qf.path("TT") == "fused"
+    monkeypatch.setenv("ORPHX_QE", "cufft")
+    qc = lensing.qest(shape, wcs, cosmology.default_theory(), **kw)
+    assert qc.path("TT") == "half"
+    monkeypatch.delenv("ORPHX_QE")
+    rng = np.random.RandomState(11)
+    T = rng.standard_normal((2,) + tuple(shape)) * 50
+    for q in (qf, qc):
+        q.reset_meanfield("TT")
+    a = qf.kappa_from_maps("TT", T, returnFt=True, accumulate_meanfield=True)
+    b = qc.kappa_from_maps("TT", T, returnFt=True, accumulate_meanfield=True)
+    assert relerr(a, b) < TOL64
+    assert relerr(qf.meanfield("TT")[0], qc.meanfield("TT")[0]) < TOL64
+    assert relerr(qf.kappa_from_maps("TT", T), qc.kappa_from_maps("TT", T)) < TOL64
+    assert relerr(qf.kappa_from_map("TT", np.fft.fft2(T[0]), alreadyFTed=True), qc.kappa_from_map("TT", T[0])) < TOL64
+
+
+@pytest.mark.parametrize("npix", [128, 512])
+def test_fp32_mode(npix, theory):
     from orphics_b200 import lensing, cosmology
-    shape, wcs, so, wo, q, qo = setup(128, 2.0, theory, True)
+    shape, wcs, so, wo, q, qo = setup(npix, 2.0, theory, True)
     q32 = lensing.qest(shape, wcs, cosmology.default_theory(), noise2d=qo.N.noise["TT"], beam2d=qo.N.beam,
                        kmask=qo.N.fmask["TT"], kmask_K=qo.N.fmaskK, unlensed_equals_lensed=True, dtype=np.float32)
     rng = np.random.RandomState(5)
     T = (rng.standard_normal(shape) * 50).astype(np.float32)
+    assert q32.path("TT") == ("fused" if npix >= 512 else "half")
     k = q32.kappa_from_map("TT", T)
     assert k.dtype == np.float32
     assert relerr(k, qo.kappa_from_map("TT", T.astype(np.float64))) < 20 * TOL32   # quadratic in fp32 data
