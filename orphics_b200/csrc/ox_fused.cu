@@ -49,15 +49,23 @@ namespace {
 constexpr int minb_for(int threads, int regs) { return regs > 0 && 65536 / (threads * regs) > 1 ? 65536 / (threads * regs) : 1; }
 
 // ---- shared helpers -------------------------------------------------------------------
+// 1/x for normal positive x to ~1 ulp without the IEEE division's slow-path branch (which would split
+// the straight-line pixel code): MUFU seed (2^-20) + two Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+
+// cos/sin of the Q/U <-> E/B rotation angle 2 phi_l (enmap.queb_rotmat; healpix sign unless iau)
 __device__ __forceinline__ void rot_cs(double y, double x, double sgn, double &c, double &s) {
-  double l2 = y * y + x * x;
-  c = 1.0;
-  s = 0.0;
-  if (l2 > 0.0) {
-    double inv = 1.0 / l2;
-    c = (y * y - x * x) * inv;
-    s = sgn * (-2.0 * x * y) * inv;
-  }
+  const double l2 = y * y + x * x;
+  const bool nz = l2 > 0.0;
+  const double inv = fast_rcp(nz ? l2 : 1.0);
+  c = nz ? (y * y - x * x) * inv : 1.0;
+  s = sgn * (-2.0 * x * y) * inv;
 }
 
 // deterministic in-warp reduce-by-key: afterwards the lowest lane of every group of equal keys
@@ -98,9 +106,13 @@ struct SimColArgs {
 // Hermitian part of the simulated Fourier field at pixel (iy, ix) of the half plane:
 // z[c] = 1/2 [k_c(p) + conj k_c(p')] / sqrt(N), k = covsqrt . r [rotated EB -> QU]
 // (MapGen.get_map, maps.py:1576-1587, followed by enmap.ifft(...).real)
-// INTERIOR: the column is neither ix = 0 nor the Nyquist column, so no pixel is its own mirror image
-// and the canonical member of each pair {p, p'} is decided by the row alone
-template <typename T, int NC, int MODE, bool INTERIOR>
+// PATH >= 1 (interior): the column is neither ix = 0 nor the Nyquist column, so no pixel is its own
+// mirror image and the canonical member of each pair {p, p'} is decided by the row alone.
+// PATH == 2 (interior, covsqrt(p') = covsqrt(p), Hermitian noise): k(p') = conj k(p) before the
+// rotation and the rotation at p' has the same cosine and the same sine -- except on the Nyquist row,
+// where the sine flips -- so 1/2 [k(p) + conj k(p')] = rotation of k(p) with the sine zeroed on that
+// row: the mirrored pixel is never touched (half the mixing, one rotation instead of two)
+template <typename T, int NC, int MODE, int PATH>
 __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::PhiloxKeys &keys, const double2 *logtab,
                                           const double *noise_sim, int ix, int mxp, int iy, double h,
                                           typename V2<T>::type (&z)[NC]) {
@@ -108,11 +120,13 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
   const unsigned n = (unsigned)a.ny * (unsigned)a.nx;
   const unsigned p = (unsigned)iy * a.nx + ix, q = (unsigned)my * a.nx + mxp;
   const unsigned tp = (unsigned)ix * a.ny + iy, tq = (unsigned)mxp * a.ny + my;
+  constexpr bool INTERIOR = PATH >= 1;
+  constexpr bool ONESIDED = PATH == 2 && MODE == OX_NOISE_PHILOX_HERMITIAN;
   T covp[NC * NC], covq[NC * NC];
 #pragma unroll
   for (int e = 0; e < NC * NC; e++) {
     covp[e] = a.covT[(size_t)e * n + tp];
-    covq[e] = a.cov_symmetric ? covp[e] : a.covT[(size_t)e * n + tq];
+    covq[e] = (ONESIDED || a.cov_symmetric) ? covp[e] : a.covT[(size_t)e * n + tq];
   }
   double pr[NC], pi[NC], qr[NC], qi[NC];
   if (MODE == OX_NOISE_HOST) {
@@ -142,6 +156,34 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
       qr[c] = pr[c];
       qi[c] = -pi[c];
     }
+  }
+  if (ONESIDED) {
+    double kr[NC], ki[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+      double sr = 0, si = 0;
+#pragma unroll
+      for (int j = 0; j < NC; j++) {
+        const double cp = (double)covp[i * NC + j];
+        sr += cp * pr[j]; si += cp * pi[j];
+      }
+      kr[i] = sr; ki[i] = si;
+    }
+    if (NC == 3 && a.rot) {
+      double c, sn;
+      rot_cs(a.ly[iy], a.lx[ix], a.rot_sgn, c, sn);
+      if (2 * iy == a.ny) sn = 0.0;
+      const double t1 = c * kr[1] + sn * kr[2], t2 = c * ki[1] + sn * ki[2];
+      const double t3 = -sn * kr[1] + c * kr[2], t4 = -sn * ki[1] + c * ki[2];
+      kr[1] = t1; ki[1] = t2; kr[2] = t3; ki[2] = t4;
+    }
+    const double h2 = 2.0 * h;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      z[c].x = (T)(h2 * kr[c]);
+      z[c].y = (T)(h2 * ki[c]);
+    }
+    return;
   }
   // k(p) = covsqrt(p) r(p), k(p') = covsqrt(p') r(p')
   double kpr[NC], kpi[NC], kqr[NC], kqi[NC];
@@ -205,30 +247,40 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
     // straight-line code (16 independent Philox/Box-Muller chains for the scheduler to interleave),
     // no staging in shared memory
     T2 v[16];
-    if (ix != 0 && ix != a.mx) {
-#pragma unroll
-      for (int m = 0; m < 16; m++) {
-        T2 z[NC];
-        sim_pixel<T, NC, MODE, true>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);
-        v[m] = z[0];
-      }
+    const bool interior = ix != 0 && ix != a.mx;
+#define OX_GEN16(PATH)                                                                        \
+  _Pragma("unroll") for (int m = 0; m < 16; m++) {                                            \
+    T2 z[NC];                                                                                 \
+    sim_pixel<T, NC, MODE, PATH>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);      \
+    v[m] = z[0];                                                                              \
+  }
+    if (interior && a.cov_symmetric && MODE == OX_NOISE_PHILOX_HERMITIAN) {
+      OX_GEN16(2)
+    } else if (interior) {
+      OX_GEN16(1)
     } else {
-#pragma unroll
-      for (int m = 0; m < 16; m++) {
-        T2 z[NC];
-        sim_pixel<T, NC, MODE, false>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);
-        v[m] = z[0];
-      }
+      OX_GEN16(0)
     }
+#undef OX_GEN16
     RegLoad<T2> ld{v};
     FFT::template run<+1, false, false>(s, tws, u, 0, ld, st);
   } else {
+    if (ix != 0 && ix != a.mx && a.cov_symmetric && MODE == OX_NOISE_PHILOX_HERMITIAN) {
 #pragma unroll 2
-    for (int iy = tid; iy < LY; iy += NTHREADS) {
-      T2 z[NC];
-      sim_pixel<T, NC, MODE, false>(a, keys, logtab, noise_sim, ix, mxp, iy, h, z);
+      for (int iy = tid; iy < LY; iy += NTHREADS) {
+        T2 z[NC];
+        sim_pixel<T, NC, MODE, 2>(a, keys, logtab, noise_sim, ix, mxp, iy, h, z);
 #pragma unroll
-      for (int c = 0; c < NC; c++) s[c * PS + pad(iy)] = z[c];
+        for (int c = 0; c < NC; c++) s[c * PS + pad(iy)] = z[c];
+      }
+    } else {
+#pragma unroll 2
+      for (int iy = tid; iy < LY; iy += NTHREADS) {
+        T2 z[NC];
+        sim_pixel<T, NC, MODE, 0>(a, keys, logtab, noise_sim, ix, mxp, iy, h, z);
+#pragma unroll
+        for (int c = 0; c < NC; c++) s[c * PS + pad(iy)] = z[c];
+      }
     }
     __syncthreads();
     const int bar = (NT % 32 == 0) ? 1 + f : 0;
