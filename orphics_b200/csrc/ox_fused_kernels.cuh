@@ -3,11 +3,16 @@
 // r2c on tiles of R rows of a transposed half plane), a generic column kernel (load functor ->
 // FFT along y -> store functor) and their launchers.  See ox_fft.cuh for the FFT engine.
 #pragma once
+#include <stdlib.h>
+
 #include "ox_common.cuh"
 #include "ox_fft.cuh"
 
 #ifndef OX_KB_ROWS64
 #define OX_KB_ROWS64 4  // rows per CTA of the row kernel for 16-byte elements (64 B segments)
+#endif
+#ifndef OX_KB_MINB
+#define OX_KB_MINB 2    // resident CTAs per SM asked of the row kernel (CTAs of <= 256 threads)
 #endif
 
 namespace oxk {
@@ -53,6 +58,24 @@ int set_smem(F kernel, size_t bytes) {
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
+
+// bytes of L2 set aside for persisting accesses (0 = feature off: ORPHX_L2_PERSIST=0, or unsupported);
+// set once per process to half of what the device allows
+inline size_t l2_persist_budget() {
+  static long long budget = -1;
+  if (budget < 0) {
+    budget = 0;
+    const char *env = getenv("ORPHX_L2_PERSIST");
+    int dev = 0, maxp = 0;
+    if (!(env && env[0] == '0') && cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && maxp > 0) {
+      size_t want = (size_t)maxp / 2;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) budget = (long long)want;
+    }
+    cudaGetLastError();
+  }
+  return (size_t)budget;
+}
 
 // ---- K_B -------------------------------------------------------------------------------
 template <typename T>
@@ -129,7 +152,7 @@ enum { ROW_IN_H = 1, ROW_OUT_MAP = 2, ROW_WIN = 4, ROW_OUT_H = 8 };
 
 // R rows per CTA, each a length-MX complex FFT handled by NT = MX/16 threads
 template <typename T, int MX, int R, int MODE>
-__global__ void __launch_bounds__(R *(MX / 16), (R * (MX / 16) <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(R *(MX / 16), (R * (MX / 16) <= 256 ? OX_KB_MINB : 1))
 fused_row_kernel(RowArgs<T> a) {
   constexpr bool IN_H = MODE & ROW_IN_H, OUT_MAP = MODE & ROW_OUT_MAP, WIN = MODE & ROW_WIN, OUT_H = MODE & ROW_OUT_H;
   typedef typename V2<T>::type T2;
@@ -245,7 +268,28 @@ int launch_row_mode(RowArgs<T> &a, long long nplanes) {
   auto k = fused_row_kernel<T, MX, R, MODE>;
   OX_TRY(set_smem(k, smem));
   dim3 grid(a.ny / R, (unsigned)nplanes);
-  k<<<grid, R * (MX / 16), smem, g_stream>>>(a);
+  const size_t wbytes = sizeof(T) * (size_t)a.ny * a.nx;
+  if (a.window && a.win_group_stride == 0 && nplanes > 1 && l2_persist_budget() >= wbytes) {
+    // the window is shared by every plane of the launch but is evicted from L2 between its uses by the
+    // planes streaming through (ncu: K_B re-read its 32 MB from DRAM for every map): keep it resident
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(R * (MX / 16));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = g_stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<T *>(a.window);
+    attr[0].val.accessPolicyWindow.num_bytes = wbytes;
+    attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OX_CUDA(cudaLaunchKernelEx(&cfg, k, a));
+  } else {
+    k<<<grid, R * (MX / 16), smem, g_stream>>>(a);
+  }
   OX_KERNEL_CHECK();
   return OX_OK;
 }
