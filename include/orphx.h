@@ -210,6 +210,24 @@ int ox_power_filter(ox_powerplan *p, const void *maps, int where, int nbatch, co
  * out = scale * FFT_direction(in), direction -1 forward / +1 backward, nplanes arrays [ny][nx] */
 int ox_fft_c2c(ox_powerplan *p, const void *in, int where, int nplanes, int direction, double scale, void *out, int out_where);
 
+/* ---- split / cross-spectrum callers.  Arrays are full-plane [ny][nx]; npix = ny*nx.
+ * maps.split_calc (maps.py:2295-2332): isplits/jsplits complex128 [ni|nj][npix] Fourier transforms of the
+ * splits, icoadd/jcoadd complex128 [npix]; outputs float64 [npix]: total, crosses (signal estimate), noise.
+ * normfact = FourierCalc.normfact (f2power, maps.py:1620-1624). */
+int ox_split_calc(const void *isplits, const void *jsplits, const void *icoadd, const void *jcoadd, int where, int ni, int nj,
+                  long long npix, double normfact, int alt, double *total, double *crosses, double *noise, int out_where);
+/* maps.noise_from_splits (maps.py:2337-2411): splits are real maps [nsplits][ncomp][ny][nx] of the plan dtype
+ * (the caller applies the reference's float32 cast); outputs float64 [ncomp][ncomp][ny][nx]: the noise model
+ * (auto - cross)/nsplits and, with do_cross, the mean cross spectrum of the i < j split pairs ("cross_teb":
+ * the reference never applies its Q,U -> E,B rotation there, maps.py:2359,2379 -- reproduced). */
+int ox_noise_from_splits(ox_powerplan *p, const void *splits, int where, int nsplits, int ncomp, int do_cross, double *noise,
+                         double *crossteb, int out_where);
+/* lensing.SplitLensing.cross_estimator (lensing.py:980-1003): per-pixel combination of the stacked
+ * kappa_hat(l) arrays (complex of `dtype`, [1 + 3 n + n(n-1)][npix]) in the order q(s,s); for each split i:
+ * q(m_i,s), q(s,m_i), q(m_i,m_i); then for each i < j: q(m_i,m_j), q(m_j,m_i).  Output float64 [npix]. */
+int ox_split_lensing_combine(const void *khat, int where, int dtype, int nsplits, long long npix, double normfact, double *out,
+                             int out_where);
+
 #ifdef __cplusplus
 }
 #endif

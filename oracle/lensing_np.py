@@ -80,3 +80,42 @@ class FlatLensingSims:
         beamed = maps.filter_map(lensed, self.kbeam)
         noise = self.ngen.get_map(seed=seed_noise)
         return unlensed, kappa, lensed, beamed, noise, enmap.ndmap(np.asarray(beamed) + np.asarray(noise), self.wcs)
+
+
+class SplitLensing:
+    """lensing.py:959-1003: split-based four-point estimator.  qfrag(a, b) = kappa_hat(l) of the quadratic
+    estimator with Fourier-space X leg a and Y leg b (lensing.py:973-976); cross_estimator combines the
+    estimators of every pair of splits so that no noise bias from a single split survives."""
+
+    def __init__(self, shape, wcs, qest, XY="TT", fourier_calc=None):
+        from . import maps_np
+        self.fc = fourier_calc if fourier_calc is not None else maps_np.FourierCalc(shape, wcs)
+        self.qest, self.est = qest, XY
+
+    def qpower(self, k1, k2):
+        return self.fc.f2power(k1, k2)
+
+    def qfrag(self, a, b):
+        assert self.est == "TT"   # the reference's 'EE' branch is marked "wrong!" (lensing.py:977)
+        return self.qest.kappa_from_map("TT", T2DData=np.array(a), T2DDataY=np.array(b), alreadyFTed=True, returnFt=True)
+
+    def cross_estimator(self, ksplits):
+        splits = np.asanyarray(ksplits)
+        n = splits.shape[0]
+        fn = float(n)
+        s = np.mean(splits, axis=0)
+        k = self.qfrag(s, s)
+        kiisum, psum, psum2 = 0.0, 0.0, 0.0
+        for i in range(n):
+            mi = splits[i]
+            ki = (self.qfrag(mi, s) + self.qfrag(s, mi)) / 2.0
+            kii = self.qfrag(mi, mi)
+            kiisum = kiisum + kii
+            kic = ki - kii / fn
+            psum = psum + self.qpower(kic, kic)
+            for j in range(i + 1, n):
+                mj = splits[j]
+                kij = (self.qfrag(mi, mj) + self.qfrag(mj, mi)) / 2.0
+                psum2 = psum2 + self.qpower(kij, kij)
+        kc = k - kiisum / fn ** 2
+        return (fn ** 4 * self.qpower(kc, kc) - 4.0 * fn ** 2 * psum + 4.0 * psum2) / fn / (fn - 1.0) / (fn - 2.0) / (fn - 3.0)

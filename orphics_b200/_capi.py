@@ -106,6 +106,9 @@ SIGNATURES = {
     "ox_qe_path": [_vp],
     "ox_fft_c2c": [_vp, _vp, _i, _i, _i, _d, _vp, _i],
     "ox_power_filter": [_vp, _vp, _i, _i, _vp, _i, _vp, _i],
+    "ox_split_calc": [_vp, _vp, _vp, _vp, _i, _i, _i, C.c_longlong, _d, _i, _vp, _vp, _vp, _i],
+    "ox_noise_from_splits": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i],
+    "ox_split_lensing_combine": [_vp, _i, _i, _i, C.c_longlong, _d, _vp, _i],
 }
 
 for _name, _args in SIGNATURES.items():

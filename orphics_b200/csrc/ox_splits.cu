@@ -1,0 +1,243 @@
+// Split / cross-spectrum callers of the hot path: O(nsplits^2) combinations of f2power and
+// of the quadratic estimator that the reference evaluates pair by pair in Python, as single device passes.
+//   maps.split_calc            maps.py:2295-2332
+//   maps.noise_from_splits     maps.py:2337-2411
+//   lensing.SplitLensing.cross_estimator   lensing.py:980-1003 (the per-pixel combination; the estimators
+//                                           themselves run through ox_qe_reconstruct)
+// All sums run in the reference's order per pixel in double precision (no atomics).
+#include "ox_common.cuh"
+
+using namespace ox;
+
+namespace {
+
+constexpr int ST = 256;
+constexpr int MAXC = 6;  // components per split of noise_from_splits (I,Q,U of up to two arrays)
+
+// ---- split_calc: full-plane complex128 in, float64 out
+__global__ void split_calc_kernel(const double2 *__restrict__ is, const double2 *__restrict__ js, const double2 *__restrict__ ic,
+                                  const double2 *__restrict__ jc, int ni, int nj, long long n, double nf, int alt,
+                                  double *__restrict__ total, double *__restrict__ crosses, double *__restrict__ noise) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double2 A = ic[p], B = jc[p];
+  const double tot = (A.x * B.x + A.y * B.y) * nf;  // Re(conj(A) B) x normfact (f2power, maps.py:1620)
+  double cr, nz;
+  if (alt) {
+    double acc = 0.0;
+    for (int i = 0; i < ni; i++) {
+      const double2 a = is[i * n + p], b = js[i * n + p];
+      const double dx = a.x - A.x, dy = a.y - A.y, ex = b.x - B.x, ey = b.y - B.y;
+      acc += (dx * ex + dy * ey) * nf;
+    }
+    nz = acc / ((1.0 - 1.0 / ni) * (double)ni * (double)ni);
+    cr = tot - nz;
+  } else {
+    double acc = 0.0, cnt = 0.0;
+    for (int i = 0; i < ni; i++) {
+      const double2 a = is[i * n + p];
+      for (int j = 0; j < nj; j++) {
+        if (i == j) continue;
+        const double2 b = js[j * n + p];
+        acc += (a.x * b.x + a.y * b.y) * nf;
+        cnt += 1.0;
+      }
+    }
+    cr = acc / cnt;
+    nz = tot - cr;
+  }
+  total[p] = tot;
+  crosses[p] = cr;
+  noise[p] = nz;
+}
+
+// ---- noise_from_splits on half planes kh[nsplits][nc][ny][nxh]; outputs [nc][nc][ny][nx] float64
+// auto_ab = sum_s Re(conj k_s[a] k_s[b]) / n, cross_ab = sum_{i<j} Re(conj k_i[a] k_j[b]) / npairs for a <= b
+// (power2d fills the upper triangle and mirrors it, maps.py:1664-1671); noise = (auto - cross)/n.
+// "cross_teb" is the same cross spectrum: the reference never applies its Q,U -> E,B rotation (maps.py:2359,2379).
+template <typename T2>
+__global__ void noise_from_splits_kernel(const T2 *__restrict__ kh, int nsplits, int nc, int ny, int nx, int nxh, double nf,
+                                         double *__restrict__ noise, double *__restrict__ crossteb) {
+  const long long nh = (long long)ny * nxh, n = (long long)ny * nx;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= nh) return;
+  const int iy = (int)(t / nxh), ix = (int)(t - (long long)iy * nxh);
+  double pre_x[MAXC], pre_y[MAXC], au[MAXC * MAXC], cr[MAXC * MAXC];
+  for (int a = 0; a < nc; a++) pre_x[a] = pre_y[a] = 0.0;
+  for (int e = 0; e < nc * nc; e++) au[e] = cr[e] = 0.0;
+  for (int s = 0; s < nsplits; s++) {
+    double kx[MAXC], ky[MAXC];
+    for (int a = 0; a < nc; a++) {
+      const T2 z = kh[((long long)s * nc + a) * nh + t];
+      kx[a] = z.x;
+      ky[a] = z.y;
+    }
+    for (int a = 0; a < nc; a++)
+      for (int b = a; b < nc; b++) {
+        au[a * nc + b] += (kx[a] * kx[b] + ky[a] * ky[b]) * nf;
+        cr[a * nc + b] += (pre_x[a] * kx[b] + pre_y[a] * ky[b]) * nf;  // sum over earlier splits i < s
+      }
+    for (int a = 0; a < nc; a++) {
+      pre_x[a] += kx[a];
+      pre_y[a] += ky[a];
+    }
+  }
+  const double npairs = 0.5 * nsplits * (nsplits - 1.0);
+  const bool mirror = ix > 0 && 2 * ix < nx;
+  const long long p = (long long)iy * nx + ix, q = (long long)(iy ? ny - iy : 0) * nx + (nx - ix);
+  for (int a = 0; a < nc; a++)
+    for (int b = a; b < nc; b++) {
+      const double c = cr[a * nc + b] / npairs, nz = (au[a * nc + b] / nsplits - c) / nsplits;
+      const long long o1 = ((long long)a * nc + b) * n, o2 = ((long long)b * nc + a) * n;
+      noise[o1 + p] = nz;
+      noise[o2 + p] = nz;
+      if (mirror) {
+        noise[o1 + q] = nz;
+        noise[o2 + q] = nz;
+      }
+      if (crossteb) {
+        crossteb[o1 + p] = c;
+        crossteb[o2 + p] = c;
+        if (mirror) {
+          crossteb[o1 + q] = c;
+          crossteb[o2 + q] = c;
+        }
+      }
+    }
+}
+
+// ---- SplitLensing.cross_estimator: per-pixel combination of the stacked estimators
+// K[0] = q(s,s); K[1+3i], K[2+3i], K[3+3i] = q(m_i,s), q(s,m_i), q(m_i,m_i); then for i < j (row-major)
+// K[..] = q(m_i,m_j), q(m_j,m_i)                                                       (lensing.py:980-1003)
+template <typename T2>
+__global__ void split_lensing_combine_kernel(const T2 *__restrict__ K, int ns, long long n, double nf, double *__restrict__ out) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double fn = ns;
+  double sx = 0.0, sy = 0.0, psum = 0.0, psum2 = 0.0;
+  for (int i = 0; i < ns; i++) {
+    const T2 a = K[(1 + 3 * i) * n + p], b = K[(2 + 3 * i) * n + p], c = K[(3 + 3 * i) * n + p];
+    sx += c.x;
+    sy += c.y;
+    const double kx = ((double)a.x + (double)b.x) / 2.0 - (1.0 / fn) * (double)c.x;
+    const double ky = ((double)a.y + (double)b.y) / 2.0 - (1.0 / fn) * (double)c.y;
+    psum += (kx * kx + ky * ky) * nf;
+  }
+  long long idx = 1 + 3 * (long long)ns;
+  for (int i = 0; i < ns; i++)
+    for (int j = i + 1; j < ns; j++) {
+      const T2 a = K[idx * n + p], b = K[(idx + 1) * n + p];
+      idx += 2;
+      const double kx = ((double)a.x + (double)b.x) / 2.0, ky = ((double)a.y + (double)b.y) / 2.0;
+      psum2 += (kx * kx + ky * ky) * nf;
+    }
+  const T2 k0 = K[p];
+  const double cx = (double)k0.x - (1.0 / (fn * fn)) * sx, cy = (double)k0.y - (1.0 / (fn * fn)) * sy;
+  const double pc = (cx * cx + cy * cy) * nf;
+  out[p] = (fn * fn * fn * fn * pc - 4.0 * fn * fn * psum + 4.0 * psum2) / fn / (fn - 1.0) / (fn - 2.0) / (fn - 3.0);
+}
+
+unsigned blocks(long long n) { return (unsigned)((n + ST - 1) / ST); }
+
+}  // namespace
+
+extern "C" {
+
+int ox_split_calc(const void *isplits, const void *jsplits, const void *icoadd, const void *jcoadd, int where, int ni, int nj,
+                  long long npix, double normfact, int alt, double *total, double *crosses, double *noise, int out_where) {
+  OX_REQUIRE(isplits && jsplits && icoadd && jcoadd && total && crosses && noise, "ox_split_calc: null pointer");
+  OX_REQUIRE(ni >= 1 && nj >= 1 && npix >= 1, "ox_split_calc: bad sizes");
+  OX_REQUIRE(!alt || ni == nj, "split_calc(alt=True) needs as many i splits as j splits (%d vs %d)", ni, nj);
+  OX_REQUIRE(alt || ni * (long long)nj > (ni < nj ? ni : nj), "split_calc(alt=False) needs at least one i != j pair");
+  DevBuf b0, b1, b2, b3, o;
+  const void *is, *js, *ic, *jc;
+  const size_t cb = sizeof(double2) * (size_t)npix;
+  OX_TRY(stage_in(isplits, where, cb * ni, b0, &is));
+  OX_TRY(stage_in(jsplits, where, cb * nj, b1, &js));
+  OX_TRY(stage_in(icoadd, where, cb, b2, &ic));
+  OX_TRY(stage_in(jcoadd, where, cb, b3, &jc));
+  double *t = total, *c = crosses, *z = noise;
+  if (out_where == OX_HOST) {
+    OX_TRY(o.ensure(3 * sizeof(double) * (size_t)npix));
+    t = o.as<double>();
+    c = t + npix;
+    z = c + npix;
+  }
+  split_calc_kernel<<<blocks(npix), ST, 0, g_stream>>>((const double2 *)is, (const double2 *)js, (const double2 *)ic,
+                                                      (const double2 *)jc, ni, nj, npix, normfact, alt, t, c, z);
+  OX_KERNEL_CHECK();
+  if (out_where == OX_HOST) {
+    OX_TRY(stage_out(total, OX_HOST, t, sizeof(double) * (size_t)npix));
+    OX_TRY(stage_out(crosses, OX_HOST, c, sizeof(double) * (size_t)npix));
+    OX_TRY(stage_out(noise, OX_HOST, z, sizeof(double) * (size_t)npix));
+  }
+  OX_CUDA(cudaStreamSynchronize(g_stream));
+  return OX_OK;
+}
+
+int ox_noise_from_splits(ox_powerplan *p, const void *splits, int where, int nsplits, int ncomp, int do_cross, double *noise,
+                         double *crossteb, int out_where) {
+  OX_REQUIRE(p && splits && noise, "ox_noise_from_splits: null pointer");
+  OX_REQUIRE(nsplits >= 2, "noise_from_splits needs at least two splits (got %d)", nsplits);
+  OX_REQUIRE(ncomp >= 1 && ncomp <= MAXC, "noise_from_splits: ncomp must be 1..%d (got %d)", MAXC, ncomp);
+  OX_REQUIRE(!do_cross || crossteb, "do_cross needs an output for the cross spectrum");
+  ox_geometry *g = p->g;
+  const size_t es = elem_size(p->dtype);
+  const long long n = (long long)g->ny * g->nx, nh = (long long)g->ny * g->nxh;
+  const int planes = nsplits * ncomp;
+  DevBuf in, kh, o;
+  OX_TRY(in.ensure(es * (size_t)planes * n));
+  OX_TRY(kh.ensure(2 * es * (size_t)planes * nh));
+  OX_CUDA(cudaMemcpyAsync(in.p, splits, es * (size_t)planes * n, where == OX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                          g_stream));
+  OX_TRY(p->fft.exec_r2c(planes, in.p, kh.p));   // iqu2teb(normalize=False, rot=False), maps.py:2371
+  const size_t ob = sizeof(double) * (size_t)ncomp * ncomp * n;
+  double *dn = noise, *dc = crossteb;
+  if (out_where == OX_HOST) {
+    OX_TRY(o.ensure(2 * ob));
+    dn = o.as<double>();
+    dc = do_cross ? dn + (size_t)ncomp * ncomp * n : nullptr;
+  } else if (!do_cross) {
+    dc = nullptr;
+  }
+  if (p->dtype == OX_F64)
+    noise_from_splits_kernel<double2><<<blocks(nh), ST, 0, g_stream>>>(kh.as<double2>(), nsplits, ncomp, g->ny, g->nx, g->nxh,
+                                                                       p->normfact, dn, dc);
+  else
+    noise_from_splits_kernel<float2><<<blocks(nh), ST, 0, g_stream>>>(kh.as<float2>(), nsplits, ncomp, g->ny, g->nx, g->nxh,
+                                                                      p->normfact, dn, dc);
+  OX_KERNEL_CHECK();
+  if (out_where == OX_HOST) {
+    OX_TRY(stage_out(noise, OX_HOST, dn, ob));
+    if (do_cross) OX_TRY(stage_out(crossteb, OX_HOST, dc, ob));
+  }
+  OX_CUDA(cudaStreamSynchronize(g_stream));
+  return OX_OK;
+}
+
+int ox_split_lensing_combine(const void *khat, int where, int dtype, int nsplits, long long npix, double normfact, double *out,
+                             int out_where) {
+  OX_REQUIRE(khat && out, "ox_split_lensing_combine: null pointer");
+  OX_REQUIRE(nsplits >= 4, "cross_estimator needs at least four splits (got %d): its normalisation divides by (n-3)", nsplits);
+  OX_REQUIRE(dtype == OX_F64 || dtype == OX_F32, "bad dtype %d", dtype);
+  const long long nk = 1 + 3LL * nsplits + (long long)nsplits * (nsplits - 1);
+  const size_t cb = 2 * elem_size(dtype) * (size_t)npix;
+  DevBuf b, o;
+  const void *K;
+  OX_TRY(stage_in(khat, where, cb * (size_t)nk, b, &K));
+  double *d = out;
+  if (out_where == OX_HOST) {
+    OX_TRY(o.ensure(sizeof(double) * (size_t)npix));
+    d = o.as<double>();
+  }
+  if (dtype == OX_F64)
+    split_lensing_combine_kernel<double2><<<blocks(npix), ST, 0, g_stream>>>((const double2 *)K, nsplits, npix, normfact, d);
+  else
+    split_lensing_combine_kernel<float2><<<blocks(npix), ST, 0, g_stream>>>((const float2 *)K, nsplits, npix, normfact, d);
+  OX_KERNEL_CHECK();
+  if (out_where == OX_HOST) OX_TRY(stage_out(out, OX_HOST, d, sizeof(double) * (size_t)npix));
+  OX_CUDA(cudaStreamSynchronize(g_stream));
+  return OX_OK;
+}
+
+}  // extern "C"

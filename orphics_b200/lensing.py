@@ -234,6 +234,72 @@ class qest(object):
             pass
 
 
+class SplitLensing(object):
+    """Split-based lensing power estimator (lensing.py:959-1003).  qfrag(a, b) is kappa_hat(l) of the
+    quadratic estimator with Fourier-space X leg a and Y leg b; cross_estimator combines the estimators of
+    all pairs of splits.  Here the 1 + 3n + n(n-1) estimators run as batches on the device (splits uploaded
+    once, kappa_hat(l) kept in HBM) and the per-pixel combination is one kernel (ox_split_lensing_combine)."""
+
+    def __init__(self, shape, wcs, qest, XY="TT"):
+        from . import maps
+        self.fc = maps.FourierCalc(shape, wcs)
+        self.qest = qest
+        self.est = XY
+        if XY != "TT":
+            raise NotImplementedError("SplitLensing: only the TT estimator (the reference marks its EE branch 'wrong!')")
+
+    def qpower(self, k1, k2):
+        return self.fc.f2power(k1, k2)
+
+    def qfrag(self, a, b):
+        return self.qest.kappa_from_map(self.est, T2DData=np.array(a), T2DDataY=np.array(b), alreadyFTed=True, returnFt=True)
+
+    def cross_estimator(self, ksplits):
+        q = self.qest
+        splits = np.asanyarray(ksplits)
+        n = int(splits.shape[0])
+        if n < 4:
+            raise ValueError("cross_estimator needs at least four splits (its normalisation divides by n-3)")
+        g = q.geometry.shape
+        if tuple(splits.shape[1:]) != tuple(g):
+            raise ValueError(f"ksplits of shape {splits.shape} do not match geometry {g}")
+        if self.est not in q._plans:
+            q._make_plan(self.est)
+        h = q._plans[self.est][0]
+        cdt = _capi.np_cdtype(q.dtype)
+        npix = g[0] * g[1]
+        plane = npix * np.dtype(cdt).itemsize
+        maps_h = np.empty((n + 1,) + tuple(g), dtype=cdt)          # m_0 .. m_{n-1}, then the mean s
+        maps_h[:n] = splits
+        maps_h[n] = np.mean(splits, axis=0)
+        M = _capi.DeviceBuffer(maps_h.nbytes).upload(maps_h)
+        S = n
+        pairs = [(S, S)]
+        for i in range(n):
+            pairs += [(i, S), (S, i), (i, i)]
+        for i in range(n):
+            for j in range(i + 1, n):
+                pairs += [(i, j), (j, i)]
+        nb = q.max_batch
+        K = _capi.DeviceBuffer(len(pairs) * plane)
+        X, Y = _capi.DeviceBuffer(nb * plane), _capi.DeviceBuffer(nb * plane)
+        try:
+            for c0 in range(0, len(pairs), nb):
+                chunk = pairs[c0:c0 + nb]
+                for t, (ia, ib) in enumerate(chunk):
+                    check(lib.ox_memcpy_d2d(C.c_void_p(X.ptr + t * plane), C.c_void_p(M.ptr + ia * plane), plane))
+                    check(lib.ox_memcpy_d2d(C.c_void_p(Y.ptr + t * plane), C.c_void_p(M.ptr + ib * plane), plane))
+                check(lib.ox_qe_reconstruct(h, C.c_void_p(X.ptr), C.c_void_p(Y.ptr), _capi.OX_DEVICE, len(chunk), 1, 1, 0,
+                                            C.c_void_p(K.ptr + c0 * plane), _capi.OX_DEVICE))
+            out = np.empty(g, dtype=np.float64)
+            check(lib.ox_split_lensing_combine(C.c_void_p(K.ptr), _capi.OX_DEVICE, q.dtype, n, npix, C.c_double(self.fc.normfact),
+                                               ptr(out), OX_HOST))
+        finally:
+            for b in (M, K, X, Y):
+                b.free()
+        return out
+
+
 # ---------------------------------------------------------------------------------------------
 # callers of the hot path: kappa <-> phi (lensing.py:651-665), Taylens (lensing.py:395-440),
 # FlatLensingSims (lensing.py:458-521)

@@ -471,6 +471,61 @@ def mask_kspace(shape, wcs, lxcut=None, lycut=None, lmin=None, lmax=None, method
     return ndmap(g.mask_kspace(lxcut, lycut, lmin, lmax).astype(int), wcs)
 
 
+def split_calc(isplits, jsplits, icoadd, jcoadd, fourier_calc=None, alt=True):
+    """Best estimate of the signal (mean of crosses) and of the noise (total - crosses) power from the
+    Fourier transforms (nsplits, Ny, Nx) of windowed splits and of their coadds (maps.py:2295-2332).
+    One device pass over the pixels instead of the reference's O(nsplits^2) f2power calls."""
+    a = np.asarray(isplits)
+    assert a.ndim == 3
+    wcs = getattr(isplits, "wcs", None)
+    fc = fourier_calc if fourier_calc is not None else FourierCalc(a.shape[-2:], wcs)
+    b = np.asarray(jsplits)
+    if alt:
+        assert a.shape[0] == b.shape[0]
+    cdt = np.complex128
+    a, b = np.ascontiguousarray(a, dtype=cdt), np.ascontiguousarray(b, dtype=cdt)
+    ic, jc = np.ascontiguousarray(icoadd, dtype=cdt), np.ascontiguousarray(jcoadd, dtype=cdt)
+    if a.shape[1:] != b.shape[1:] or ic.shape != a.shape[1:] or jc.shape != a.shape[1:]:
+        raise ValueError("split_calc: splits and coadds must share one (Ny, Nx) shape")
+    npix = ic.size
+    out = np.empty((3,) + ic.shape, dtype=np.float64)
+    check(lib.ox_split_calc(ptr(a), ptr(b), ptr(ic), ptr(jc), OX_HOST, a.shape[0], b.shape[0], npix, C.c_double(fc.normfact),
+                            int(bool(alt)), ptr(out[0]), ptr(out[1]), ptr(out[2]), OX_HOST))
+    w = fc.wcs if wcs is None else wcs
+    return ndmap(out[0], w), ndmap(out[1], w), ndmap(out[2], w)
+
+
+def noise_from_splits(splits, fourier_calc=None, nthread=0, do_cross=True):
+    """Noise power (auto - cross of splits)/nsplits of the I,Q,U components and the mean cross spectrum of
+    the split pairs, from (nsplits, ncomp, Ny, Nx) or (nsplits, Ny, Nx) maps (maps.py:2337-2411).  As in
+    the reference the splits are cast to float32 first (maps.py:2355) and its "T,E,B" cross spectrum is in
+    fact the unrotated I,Q,U one (the rotation branch of maps.py:2379 can never be taken).  All
+    nsplits*ncomp transforms and the O(nsplits^2) pair sums are one batched FFT and one kernel."""
+    wcs = getattr(splits, "wcs", None)
+    if wcs is None:
+        wcs = getattr(splits[0], "wcs", None)
+    arr = np.asarray(splits).astype(np.float32)
+    assert arr.ndim == 3 or arr.ndim == 4
+    if arr.ndim == 3:
+        arr = arr[:, None, :, :]
+    nsplits, ncomp = arr.shape[:2]
+    if fourier_calc is None:
+        fourier_calc = FourierCalc(arr.shape[-3:] if do_cross else arr.shape[-2:], wcs)
+    fc = fourier_calc
+    if do_cross:
+        assert ncomp == 3 or ncomp == 1
+    if arr.shape[-2:] != fc.geometry.shape:
+        raise ValueError(f"splits of shape {arr.shape} do not match geometry {fc.geometry.shape}")
+    stack = np.ascontiguousarray(arr, dtype=_capi.np_dtype(fc.dtype))
+    noise = np.empty((ncomp, ncomp) + fc.geometry.shape, dtype=np.float64)
+    cross = np.empty_like(noise) if do_cross else None
+    check(lib.ox_noise_from_splits(fc._plan(min(ncomp, 3)), ptr(stack), OX_HOST, nsplits, ncomp, int(bool(do_cross)), ptr(noise),
+                                   ptr(cross), OX_HOST))
+    if ncomp == 1:
+        return ndmap(noise[0, 0], wcs), (ndmap(cross[0, 0], wcs) if do_cross else None)
+    return noise, cross
+
+
 def filter_map(imap, kfilter, fc=None):
     """Re(ifft(fft(imap) * kfilter)) / Npix (maps.py:1922-1923)."""
     fc = FourierCalc(imap.shape, imap.wcs) if fc is None else fc

@@ -1,6 +1,9 @@
 """Secondary benchmark (BASELINE configs[3]/[4]): TT / EB quadratic-estimator reconstructions per second
 with inputs resident in HBM, and the fraction of the SURVEY 8d roofline (TT: 38 s N bytes per
-realisation incl. the mean-field accumulate; EB ~ 76 s N).  Usage: python tools/bench_qe.py [npix] [batch] [f64|f32] [TT|EB]"""
+realisation incl. the mean-field accumulate; EB ~ 76 s N).  Usage: python tools/bench_qe.py [npix] [batch] [f64|f32] [TT|EB] [nreal]
+Under torchrun (WORLD_SIZE > 1) the nreal realisations (default 10 steps x batch per rank) are split over the
+ranks with the reference's rule (mpi.py:78-91) and the mean-field stack + count are summed with one NCCL
+all-reduce each inside the timed region (BASELINE configs[3]: 512 realisations plus mean-field allreduce)."""
 import ctypes as C
 import json
 import os
@@ -9,13 +12,16 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from orphics_b200 import _capi, maps, lensing, cosmology  # noqa: E402
+from orphics_b200 import _capi, maps, lensing, cosmology, mpi  # noqa: E402
 from orphics_b200._capi import lib, check, ptr  # noqa: E402
 
 npix = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 nb = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 dt = sys.argv[3] if len(sys.argv) > 3 else "f64"
 est = sys.argv[4] if len(sys.argv) > 4 else "TT"
+rank, local, ws = mpi.init_process_group()
+_capi.require_device()
+_capi.set_device(local)
 rdt = np.float32 if dt == "f32" else np.float64
 cdt = np.complex64 if dt == "f32" else np.complex128
 s = 4 if dt == "f32" else 8
@@ -49,25 +55,68 @@ def step():
                                 C.c_void_p(out.ptr), _capi.OX_DEVICE))
 
 
+class _DevView:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+nreal = int(sys.argv[5]) if len(sys.argv) > 5 else 10 * nb * ws
+mine = len(mpi.mpi_distribute(nreal, ws)[1][rank])
+K = max(1, mine // nb)
+mf_tensors = None
+if ws > 1:
+    import torch
+    import torch.distributed as dist
+    acc, cnt, nel = C.c_void_p(), C.c_void_p(), C.c_longlong()
+    check(lib.ox_qe_meanfield(h, C.byref(acc), C.byref(cnt), C.byref(nel)))
+    mf_tensors = [torch.as_tensor(_DevView(acc.value, (2 * nel.value,), "<f8"), device=f"cuda:{local}"),
+                  torch.as_tensor(_DevView(cnt.value, (1,), "<i8"), device=f"cuda:{local}")]
 for _ in range(3):
     step()
+if ws > 1:
+    for t_ in mf_tensors:
+        dist.all_reduce(t_)
+check(lib.ox_qe_meanfield_reset(h))
 _capi.synchronize()
+if ws > 1:
+    dist.barrier()
+    torch.cuda.synchronize()
 t = _capi.Timer()
-K = 10
 l0 = _capi.launch_count()
 t.start()
 for _ in range(K):
     step()
 t.stop()
 ms = t.elapsed_ms()
-rate = K * nb / (ms / 1e3)
+ar_ms = 0.0
+if ws > 1:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t_ in mf_tensors:                 # Statistics.add_stack / allreduce (stats.py:1227-1228) over NCCL, in place
+        dist.all_reduce(t_)
+    e1.record()
+    torch.cuda.synchronize()
+    ar_ms = e0.elapsed_time(e1)
+    tt = torch.tensor([ms + ar_ms], device=f"cuda:{local}", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    count = int(mf_tensors[1].item())
+else:
+    total_ms = ms
+    count = K * nb
+rate = ws * K * nb / (total_ms / 1e3)
 bytes_per = (38 if est == "TT" else 76) * s * N
 peak = 6550.1
 try:
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
-print(json.dumps({"metric": f"{est} QE reconstructions/s at {npix}^2 {dt} (kappa_hat(l) + mean-field accumulate, inputs in HBM)",
-                  "value": rate, "ms_per_realisation": ms / (K * nb), "batch": nb, "half_plane_path": bool(real_path),
-                  "algorithmic_bytes_per_realisation": bytes_per, "roofline_frac": rate * bytes_per / 1e9 / peak,
-                  "peak_gbs": peak, "gpu_launches": _capi.launch_count() - l0, "device": _capi.device_name()}))
+if rank == 0:
+    print(json.dumps({"metric": f"{est} QE reconstructions/s at {npix}^2 {dt} (kappa_hat(l) + mean-field accumulate, inputs in HBM)",
+                      "value": rate, "n_gpus": ws, "realisations": ws * K * nb, "meanfield_count_after_allreduce": count,
+                      "ms_per_realisation_per_gpu": ms / (K * nb), "meanfield_allreduce_ms": ar_ms, "batch": nb,
+                      "path": q.path(est), "algorithmic_bytes_per_realisation": bytes_per,
+                      "roofline_frac": rate / ws * bytes_per / 1e9 / peak, "peak_gbs": peak,
+                      "gpu_launches": _capi.launch_count() - l0, "device": _capi.device_name()}))
+if ws > 1:
+    dist.destroy_process_group()
