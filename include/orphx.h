@@ -228,6 +228,14 @@ int ox_noise_from_splits(ox_powerplan *p, const void *splits, int where, int nsp
 int ox_split_lensing_combine(const void *khat, int where, int dtype, int nsplits, long long npix, double normfact, double *out,
                              int out_where);
 
+/* Fourier-space internal linear combination (maps.py:1952-2050), one pass over the pixels:
+ * mode 0 silc, 1 cilc -> complex128 [npix]; 2 silc_noise, 3 cilc_noise -> float64 [npix].
+ * kmaps complex128 [nfreq][npix] (modes 0, 1), cinv float64 [nfreq][nfreq][npix] (npix = Ny*Nx for 2-D
+ * k-space matrices or the number of bins for 1-D spectra), response vectors float64 [nfreq] on the HOST
+ * (response_a NULL = ones, the CMB).  np.nan_to_num semantics as in the reference. */
+int ox_ilc(const void *kmaps, const double *cinv, const double *response_a, const double *response_b, int nfreq, long long npix,
+           int where, int mode, void *out, int out_where);
+
 #ifdef __cplusplus
 }
 #endif

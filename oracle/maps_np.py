@@ -277,3 +277,54 @@ def noise_from_splits(splits, fourier_calc=None, do_cross=True):
     if do_cross:
         cross_teb = cross_teb / npairs
     return (auto - cross) / n, cross_teb
+
+
+# ---- Fourier-space internal linear combination (maps.py:1952-2050): per-pixel small linear algebra
+def _nan_to_num(x):
+    return np.nan_to_num(x)
+
+
+def ilc_comb_a_b(response_a, response_b, cinv):
+    """a^T Cinv b per pixel (maps.py:2046-2049): sum_l a_l (sum_k b_k Cinv[k,l]), NaN -> 0, +-inf -> +-max."""
+    inner = np.tensordot(np.asarray(response_b), np.asarray(cinv), axes=(0, 0))
+    return _nan_to_num(np.tensordot(np.asarray(response_a), inner, axes=(0, 0)))
+
+
+def ilc_map_term(kmaps, cinv, response):
+    """response^T Cinv kmaps per pixel (maps.py:2042-2044)."""
+    ck = np.sum(np.asarray(cinv) * np.asarray(kmaps)[None], axis=1)
+    return np.tensordot(np.asarray(response), ck, axes=(0, 0))
+
+
+def silc_noise(cinv, response=None):
+    """maps.py:2020-2023."""
+    response = np.ones(np.shape(cinv)[0]) if response is None else response
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return _nan_to_num(1.0 / ilc_comb_a_b(response, response, cinv))
+
+
+def silc(kmaps, cinv, response=None):
+    """Standard ILC estimate (maps.py:1952-1974)."""
+    response = np.ones(np.shape(cinv)[0]) if response is None else response
+    return ilc_map_term(kmaps, cinv, response) * silc_noise(cinv, response)
+
+
+def cilc(kmaps, cinv, response_a, response_b):
+    """Constrained ILC: component a with component b projected out (maps.py:1976-2005)."""
+    brb = ilc_comb_a_b(response_b, response_b, cinv)
+    arb = ilc_comb_a_b(response_a, response_b, cinv)
+    ara = ilc_comb_a_b(response_a, response_a, cinv)
+    arM = ilc_map_term(kmaps, cinv, response_a)
+    brM = ilc_map_term(kmaps, cinv, response_b)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return _nan_to_num((brb * arM - arb * brM) / (ara * brb - arb ** 2.0))
+
+
+def cilc_noise(cinv, response_a, response_b):
+    """maps.py:2025-2039."""
+    brb = ilc_comb_a_b(response_b, response_b, cinv)
+    ara = ilc_comb_a_b(response_a, response_a, cinv)
+    arb = ilc_comb_a_b(response_a, response_b, cinv)
+    bra = ilc_comb_a_b(response_b, response_a, cinv)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return _nan_to_num((brb ** 2.0 * ara + arb ** 2.0 * brb - brb * arb * arb - arb * brb * bra) / (ara * brb - arb ** 2.0) ** 2.0)

@@ -241,3 +241,117 @@ int ox_split_lensing_combine(const void *khat, int where, int dtype, int nsplits
 }
 
 }  // extern "C"
+
+// ---- Fourier-space ILC (maps.py:1952-2050): per-pixel small linear algebra over nfreq <= 16 channels
+namespace {
+
+constexpr int ILC_MAXF = 16;
+struct IlcResp {
+  double a[ILC_MAXF], b[ILC_MAXF];
+};
+
+__device__ __forceinline__ double nan_to_num(double x) {  // np.nan_to_num: NaN -> 0, +-inf -> +-DBL_MAX
+  if (isnan(x)) return 0.0;
+  if (isinf(x)) return x > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+  return x;
+}
+
+// a^T Cinv b = sum_l a_l (sum_k b_k Cinv[k][l])   (ilc_comb_a_b, maps.py:2046-2049)
+__device__ __forceinline__ double comb(const double *ra, const double *rb, const double *__restrict__ cinv, int nf, long long n,
+                                       long long p) {
+  double acc = 0.0;
+  for (int l = 0; l < nf; l++) {
+    double inner = 0.0;
+    for (int k = 0; k < nf; k++) inner += rb[k] * cinv[((long long)k * nf + l) * n + p];
+    acc += ra[l] * inner;
+  }
+  return nan_to_num(acc);
+}
+
+// r^T Cinv kmaps = sum_k r_k (sum_l Cinv[k][l] kmaps[l])   (ilc_map_term, maps.py:2042-2044)
+__device__ __forceinline__ double2 map_term(const double *r, const double *__restrict__ cinv, const double2 *__restrict__ km,
+                                            int nf, long long n, long long p) {
+  double2 acc = make_double2(0.0, 0.0);
+  for (int k = 0; k < nf; k++) {
+    double ix = 0.0, iy = 0.0;
+    for (int l = 0; l < nf; l++) {
+      const double c = cinv[((long long)k * nf + l) * n + p];
+      const double2 z = km[(long long)l * n + p];
+      ix += c * z.x;
+      iy += c * z.y;
+    }
+    acc.x += r[k] * ix;
+    acc.y += r[k] * iy;
+  }
+  return acc;
+}
+
+// mode 0 silc, 1 cilc (complex out), 2 silc_noise, 3 cilc_noise (real out)
+__global__ void ilc_kernel(const double2 *__restrict__ km, const double *__restrict__ cinv, IlcResp r, int nf, long long n, int mode,
+                           double *__restrict__ out) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (mode == 0 || mode == 2) {
+    const double noise = nan_to_num(1.0 / comb(r.a, r.a, cinv, nf, n, p));
+    if (mode == 2) {
+      out[p] = noise;
+      return;
+    }
+    const double2 w = map_term(r.a, cinv, km, nf, n, p);
+    // complex x real as numpy does it: (w.x + i w.y)(noise + 0 i)
+    reinterpret_cast<double2 *>(out)[p] = make_double2(w.x * noise - w.y * 0.0, w.x * 0.0 + w.y * noise);
+    return;
+  }
+  const double brb = comb(r.b, r.b, cinv, nf, n, p), arb = comb(r.a, r.b, cinv, nf, n, p), ara = comb(r.a, r.a, cinv, nf, n, p);
+  if (mode == 3) {
+    const double bra = comb(r.b, r.a, cinv, nf, n, p);
+    const double numer = brb * brb * ara + arb * arb * brb - brb * arb * arb - arb * brb * bra;
+    const double d = ara * brb - arb * arb;
+    out[p] = nan_to_num(numer / (d * d));
+    return;
+  }
+  const double2 arM = map_term(r.a, cinv, km, nf, n, p), brM = map_term(r.b, cinv, km, nf, n, p);
+  const double nx = brb * arM.x - arb * brM.x, ny = brb * arM.y - arb * brM.y;
+  const double norm = ara * brb - arb * arb;
+  double ox, oy;
+  if (norm == 0.0) {  // numpy's complex division by (0 + 0i): componentwise x / 0
+    ox = nx / 0.0;
+    oy = ny / 0.0;
+  } else {            // numpy's complex division by (norm + 0i): multiply by the reciprocal
+    const double scl = 1.0 / norm;
+    ox = nx * scl;
+    oy = ny * scl;
+  }
+  reinterpret_cast<double2 *>(out)[p] = make_double2(nan_to_num(ox), nan_to_num(oy));
+}
+
+}  // namespace
+
+extern "C" int ox_ilc(const void *kmaps, const double *cinv, const double *response_a, const double *response_b, int nfreq,
+                      long long npix, int where, int mode, void *out, int out_where) {
+  OX_REQUIRE(cinv && out, "ox_ilc: null pointer");
+  OX_REQUIRE(mode >= 0 && mode <= 3, "ox_ilc: mode must be 0 (silc), 1 (cilc), 2 (silc_noise) or 3 (cilc_noise)");
+  OX_REQUIRE(nfreq >= 1 && nfreq <= ILC_MAXF, "ILC supports 1..%d frequency channels (got %d)", ILC_MAXF, nfreq);
+  OX_REQUIRE(mode >= 2 || kmaps, "silc/cilc need the Fourier maps");
+  OX_REQUIRE((mode != 1 && mode != 3) || (response_a && response_b), "cilc needs both response vectors");
+  IlcResp r;
+  for (int i = 0; i < ILC_MAXF; i++) {
+    r.a[i] = i < nfreq ? (response_a ? response_a[i] : 1.0) : 0.0;  // default CMB response: ones (maps.py:2007-2013)
+    r.b[i] = i < nfreq && response_b ? response_b[i] : 0.0;
+  }
+  DevBuf b0, b1, o;
+  const void *dk = nullptr, *dc;
+  if (kmaps) OX_TRY(stage_in(kmaps, where, sizeof(double2) * (size_t)nfreq * npix, b0, &dk));
+  OX_TRY(stage_in(cinv, where, sizeof(double) * (size_t)nfreq * nfreq * npix, b1, &dc));
+  const size_t ob = (mode <= 1 ? sizeof(double2) : sizeof(double)) * (size_t)npix;
+  void *d = out;
+  if (out_where == OX_HOST) {
+    OX_TRY(o.ensure(ob));
+    d = o.p;
+  }
+  ilc_kernel<<<blocks(npix), ST, 0, g_stream>>>((const double2 *)dk, (const double *)dc, r, nfreq, npix, mode, (double *)d);
+  OX_KERNEL_CHECK();
+  if (out_where == OX_HOST) OX_TRY(stage_out(out, OX_HOST, d, ob));
+  OX_CUDA(cudaStreamSynchronize(g_stream));
+  return OX_OK;
+}

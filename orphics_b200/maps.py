@@ -526,6 +526,55 @@ def noise_from_splits(splits, fourier_calc=None, nthread=0, do_cross=True):
     return noise, cross
 
 
+# ---- Fourier-space ILC (maps.py:1952-2050): per-pixel small linear algebra, one device pass each
+def ilc_def_response(response, cinv):
+    """Default CMB response: a vector of ones (maps.py:2007-2013)."""
+    if response is None:
+        response = np.ones((np.shape(cinv)[0],))
+    return response
+
+
+def _ilc(mode, kmaps, cinv, response_a, response_b):
+    cinv = np.ascontiguousarray(cinv, dtype=np.float64)
+    if cinv.ndim not in (3, 4) or cinv.shape[0] != cinv.shape[1]:
+        raise ValueError("cinv must be (nfreq, nfreq, Ny, Nx) or (nfreq, nfreq, nbins)")     # ilc_index, maps.py:2015-2023
+    nfreq, trail = cinv.shape[0], cinv.shape[2:]
+    npix = int(np.prod(trail))
+    ra = None if response_a is None else np.ascontiguousarray(response_a, dtype=np.float64)
+    rb = None if response_b is None else np.ascontiguousarray(response_b, dtype=np.float64)
+    for r in (ra, rb):
+        if r is not None and r.shape != (nfreq,):
+            raise ValueError("response vectors must have one entry per frequency")
+    km = None
+    if mode <= 1:
+        km = np.ascontiguousarray(kmaps, dtype=np.complex128)
+        if km.shape != (nfreq,) + trail:
+            raise ValueError(f"kmaps of shape {km.shape} do not match cinv {cinv.shape}")
+    out = np.empty(trail, dtype=np.complex128 if mode <= 1 else np.float64)
+    check(lib.ox_ilc(ptr(km), ptr(cinv), ptr(ra), ptr(rb), nfreq, npix, OX_HOST, mode, ptr(out), OX_HOST))
+    return out
+
+
+def silc(kmaps, cinv, response=None):
+    """Standard ILC of Fourier maps (nfreq, Ny, Nx) given the inverse covariance (maps.py:1952-1974)."""
+    return _ilc(0, kmaps, cinv, response, None)
+
+
+def cilc(kmaps, cinv, response_a, response_b):
+    """Constrained ILC: component a with component b projected out (maps.py:1976-2005)."""
+    return _ilc(1, kmaps, cinv, response_a, response_b)
+
+
+def silc_noise(cinv, response=None):
+    """maps.py:2025-2028."""
+    return _ilc(2, None, cinv, response, None)
+
+
+def cilc_noise(cinv, response_a, response_b):
+    """maps.py:2030-2041."""
+    return _ilc(3, None, cinv, response_a, response_b)
+
+
 def filter_map(imap, kfilter, fc=None):
     """Re(ifft(fft(imap) * kfilter)) / Npix (maps.py:1922-1923)."""
     fc = FourierCalc(imap.shape, imap.wcs) if fc is None else fc

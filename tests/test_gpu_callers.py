@@ -127,3 +127,14 @@ def test_split_lensing_fused_path_512(theory):
     got = sl.cross_estimator(ks)
     want = lensing_np.SplitLensing.cross_estimator(sl, ks)     # the restated loop, driving sl.qfrag / sl.qpower
     assert relerr(got, want) < 1e-10
+
+
+@pytest.mark.parametrize("tag", ["2d", "1d", "pair"])
+def test_ilc_matches_reference_functions(tag):
+    """maps.silc / cilc / silc_noise / cilc_noise on the device vs goldens made by the reference's own functions:
+    1e-10 on regular pixels, bit-exact nan_to_num / division-by-zero results on the degenerate ones."""
+    from orphics_b200 import maps
+    from test_oracle_callers import _ilc_check
+    _ilc_check(1e-10, tag, lambda name, *a: getattr(maps, name)(*a))
+    with pytest.raises(ValueError):
+        maps.silc(np.zeros((2, 4, 4), dtype=complex), np.zeros((3, 3, 4, 4)))

@@ -59,3 +59,28 @@ def test_split_lensing_restatement_matches_reference_body(theory):
     sl = lensing_np.SplitLensing(so, wo, q)
     got = sl.cross_estimator(G["sl_ksplits"])
     assert relerr(got, G["sl_cross_estimator"]) < 1e-11
+
+
+GI = np.load(os.path.join(ROOT, "tests", "golden", "ilc.npz"))
+
+
+def _ilc_check(fn, tag, got_of):
+    """good pixels to `fn` of the scale; the zero-matrix and NaN-matrix pixels (indices 0, 1) bit for bit, they
+    exercise the reference's nan_to_num / division-by-zero semantics.  Pixel 2 holds a rank-1 matrix whose cILC
+    normalisation ara*brb - arb^2 cancels to rounding noise: its value depends on the summation order (the reference
+    itself returns -16 there) and is not compared."""
+    for key, args in (("silc", ("k", "c")), ("silc_resp", ("k", "c", "a")), ("cilc", ("k", "c", "a", "b")),
+                      ("silc_noise", ("c",)), ("silc_noise_resp", ("c", "a")), ("cilc_noise", ("c", "a", "b"))):
+        src = {"k": GI[f"{tag}_kmaps"], "c": GI[f"{tag}_cinv"], "a": GI[f"{tag}_ra"], "b": GI[f"{tag}_rb"]}
+        with np.errstate(all="ignore"):
+            got = np.asarray(got_of(key.replace("_resp", ""), *[src[a] for a in args])).reshape(-1)
+        want = GI[f"{tag}_{key}"].reshape(-1)
+        assert got.dtype == want.dtype
+        good = slice(3, None)
+        assert np.max(np.abs(got[good] - want[good])) <= fn * np.max(np.abs(want[good])), (tag, key)
+        np.testing.assert_array_equal(got[:2], want[:2], err_msg=f"{tag} {key} degenerate pixels")
+
+
+@pytest.mark.parametrize("tag", ["2d", "1d", "pair"])
+def test_ilc_restatement_matches_reference_functions(tag):
+    _ilc_check(1e-12, tag, lambda name, *a: getattr(omaps, name)(*a))
