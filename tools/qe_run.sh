@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_callers.py -x -q -k ilc 2>&1 | tail -15
+python tools/bench_callers.py 2048 4 2>&1 | tail -1
