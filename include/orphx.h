@@ -181,8 +181,9 @@ int ox_pipeline_stats_reset(ox_pipeline *pl);
 enum { OX_QE_TT = 0, OX_QE_EB = 1 };
 /* filters are full-plane [ny][nx] float64: wxy = W_XY, wy = W_Y (filter x mask x beam, the historical
  * QuadNorm.WXY/WY), norm = the multiplier applied in kappa_from_map, N_L 2/(L(L+1)), x kmask_K.
- * real_path != 0 (TT only): the filters vanish on the Nyquist row/column and are symmetric under
- * l -> -l, so every field is real and the chain runs on half planes with r2c/c2r transforms. */
+ * real_path != 0: the filters vanish on the Nyquist row/column and are symmetric under l -> -l, so for
+ * Hermitian inputs every field is real (TT) or splits into real and imaginary parts that are each the
+ * transform of a Hermitian array (EB), and the chain runs on half planes with r2c/c2r transforms. */
 int ox_qeplan_create(ox_geometry *g, int est, const double *wxy, const double *wy, const double *norm, int where, int dtype,
                      int max_batch, int real_path, ox_qeplan **out);
 int ox_qeplan_destroy(ox_qeplan *q);
@@ -196,9 +197,11 @@ int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int
  * count, for an in-place NCCL all-reduce (Statistics.add_stack / allreduce, stats.py:1134-1158,1227-1228) */
 int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem);
 int ox_qe_meanfield_reset(ox_qeplan *q);
-/* which implementation the plan runs: 0 = full-plane c2c chain on cuFFT (EB, unsymmetric filters),
- * 1 = TT on half planes with cuFFT r2c/c2r, 2 = TT on half planes with the hand-written FFT passes
- * (power-of-two maps; ORPHX_QE=cufft in the environment selects 1 instead) */
+/* which implementation the plan runs for Hermitian inputs: 0 = full-plane c2c chain on cuFFT (unsymmetric
+ * filters, or EB on maps that are not powers of two), 1 = TT on half planes with cuFFT r2c/c2r, 2 = TT and
+ * 3 = EB on half planes with the hand-written FFT passes (power-of-two maps; ORPHX_QE=cufft in the
+ * environment disables 2 and 3).  already_ft inputs that are not Hermitian (checked on a sample of the
+ * pixels) always take the c2c chain. */
 int ox_qe_path(ox_qeplan *q);
 
 /* maps.filter_map (maps.py:1922-1923): Re(ifft(fft(m) * kfilter)) / Npix for nbatch x ncomp real maps;

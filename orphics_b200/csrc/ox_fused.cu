@@ -157,7 +157,7 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
       qi[c] = -pi[c];
     }
   }
-  if (ONESIDED) {
+  if constexpr (ONESIDED) {
     double kr[NC], ki[NC];
 #pragma unroll
     for (int i = 0; i < NC; i++) {
@@ -183,8 +183,7 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
       z[c].x = (T)(h2 * kr[c]);
       z[c].y = (T)(h2 * ki[c]);
     }
-    return;
-  }
+  } else {
   // k(p) = covsqrt(p) r(p), k(p') = covsqrt(p') r(p')
   double kpr[NC], kpi[NC], kqr[NC], kqi[NC];
 #pragma unroll
@@ -214,6 +213,7 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
   for (int c = 0; c < NC; c++) {
     z[c].x = (T)(h * (kpr[c] + kqr[c]));
     z[c].y = (T)(h * (kpi[c] - kqi[c]));
+  }
   }
 }
 

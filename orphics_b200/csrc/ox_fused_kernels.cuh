@@ -94,6 +94,10 @@ struct RowArgs {
   // two gradient legs of a realisation by its third field (group = 2, both strides 3 ny nx)
   int group = 1;
   long long map_in_group_stride = 0, win_group_stride = 0;
+  // sub-plane stride inside a group (0 = ny*nx) and an optional second product term (ROW_WIN2, map_in path):
+  // input = map_in * window + map_in2 * window2, with map_in2 / window2 addressed like map_in / window
+  long long map_in_sub_stride = 0;
+  const T *map_in2 = nullptr, *window2 = nullptr;
 };
 
 // first-stage input of the c2r transform: Z[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/Nx} (X[k] - conj X[M-k])
@@ -148,13 +152,14 @@ struct WindowKeep {
 
 // what a launch of the row kernel does, as compile-time flags: null checks inside the element loops
 // are branches that stop the compiler from issuing a thread's 16 window loads together
-enum { ROW_IN_H = 1, ROW_OUT_MAP = 2, ROW_WIN = 4, ROW_OUT_H = 8 };
+enum { ROW_IN_H = 1, ROW_OUT_MAP = 2, ROW_WIN = 4, ROW_OUT_H = 8, ROW_WIN2 = 16 };
 
 // R rows per CTA, each a length-MX complex FFT handled by NT = MX/16 threads
 template <typename T, int MX, int R, int MODE>
 __global__ void __launch_bounds__(R *(MX / 16), (R * (MX / 16) <= 256 ? OX_KB_MINB : 1))
 fused_row_kernel(RowArgs<T> a) {
   constexpr bool IN_H = MODE & ROW_IN_H, OUT_MAP = MODE & ROW_OUT_MAP, WIN = MODE & ROW_WIN, OUT_H = MODE & ROW_OUT_H;
+  constexpr bool WIN2 = MODE & ROW_WIN2;
   typedef typename V2<T>::type T2;
   typedef BlockFFT<T, MX> FFT;
   constexpr int NT = FFT::NT, NTHREADS = R * NT, PS = padded_size(MX), NX = 2 * MX;
@@ -206,11 +211,27 @@ fused_row_kernel(RowArgs<T> a) {
     FFT::template run<+1, true, false>(row, tws, u, bar, ld, wst);
   } else {
     // real map rows viewed as z[n] = x[2n] + i x[2n+1]
-    const T2 *src = reinterpret_cast<const T2 *>(a.map_in + grp * a.map_in_group_stride + ((sub * a.ny) + iy0 + f) * (long long)NX);
+    const long long sstride = a.map_in_sub_stride ? a.map_in_sub_stride : (long long)a.ny * NX;
+    const long long moff = grp * a.map_in_group_stride + sub * sstride + (long long)(iy0 + f) * NX;
+    const T2 *src = reinterpret_cast<const T2 *>(a.map_in + moff);
+    if (WIN2) {
+      const T2 *src2 = reinterpret_cast<const T2 *>(a.map_in2 + moff);
+      const T2 *win2 = reinterpret_cast<const T2 *>(a.window2 + grp * a.win_group_stride) + rowoff;
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-      const int n = u + m * NT;
-      wst(n, src[n], m);
+      for (int m = 0; m < 16; m++) {
+        const int n = u + m * NT;
+        const T2 z1 = src[n], w1 = ldg2(wst.win_row + n), z2 = src2[n], w2 = ldg2(win2 + n);
+        T2 z;
+        z.x = z1.x * w1.x + z2.x * w2.x;
+        z.y = z1.y * w1.y + z2.y * w2.y;
+        keep[m] = z;
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const int n = u + m * NT;
+        wst(n, src[n], m);
+      }
     }
   }
   if (!OUT_H) return;
@@ -358,7 +379,8 @@ int launch_col(const Ops &ops, const void *tw, int tw_len, int ncols, long long 
 
 template <typename T, class MODES>
 int launch_row_any(RowArgs<T> &a, long long nplanes, MODES modes) {
-  int mode = (a.Hin ? ROW_IN_H : 0) | (a.map_out ? ROW_OUT_MAP : 0) | (a.window ? ROW_WIN : 0) | (a.Hout ? ROW_OUT_H : 0);
+  int mode = (a.Hin ? ROW_IN_H : 0) | (a.map_out ? ROW_OUT_MAP : 0) | (a.window ? ROW_WIN : 0) | (a.Hout ? ROW_OUT_H : 0) |
+             (a.map_in2 ? ROW_WIN2 : 0);
   if (a.Hin && a.Hout) mode = ROW_IN_H | ROW_OUT_H;  // map_out / window are run-time options of the full pass
   switch (a.nx / 2) {
     case 128: return launch_row<T, 128>(a, nplanes, mode, modes);

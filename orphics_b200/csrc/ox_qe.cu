@@ -23,12 +23,14 @@ using namespace ox;
 struct ox_qeplan {
   ox_geometry *g = nullptr;
   int est = OX_QE_TT, dtype = OX_F64, max_batch = 1;
-  bool real_path = false;  // TT on half planes
+  bool real_path = false;  // the filters are symmetric and vanish at Nyquist: Hermitian inputs give real fields
   FFTPlans fft;
-  DevBuf wxy, wy, norm;    // T [ny][nx] full plane (general) or [ny][nxh] (real path)
+  DevBuf wxyF, wyF, normF; // T [ny][nx] full-plane tables (general c2c chain; always kept as the fall-back)
+  DevBuf wxy, wy, norm;    // T [ny][nxh] half-plane tables (real path)
+  DevBuf herm;             // double[2]: scratch of the Hermitian-input check
   DevBuf kx, ky;           // staged inputs (half or full plane complex)
   DevBuf in_real;          // staged real maps
-  DevBuf legs, fields, prod, pk, khat, full, out_real;
+  DevBuf legs, fields, prod, pk, khat, full, full2, out_real;
   DevBuf mf;               // double2 [ny][nxh] mean-field accumulator of kappa_hat(l)
   DevBuf mf_count;         // int64
   // hand-written FFT path (TT on half planes, power-of-two maps): tables and intermediates in the
@@ -36,6 +38,7 @@ struct ox_qeplan {
   bool fused = false;
   int tw_len = 0;
   DevBuf tw, wxyT, wyT, normT, legT;
+  int nlegs = 3;           // 3 (TT) or 6 (EB: real and imaginary parts of the spin-2 fields)
   DevBuf Hx, Hy, Kx, Ky, Lt, Pt, khT;
 };
 
@@ -268,14 +271,14 @@ struct ColPlainOps {
 template <typename T>
 struct LegsOps {
   typedef typename oxfft::V2<T>::type T2;
-  const T2 *kx, *ky;   // [nb][nxh][ny]
-  const T *legT;       // [3][nxh][ny]: W_XY/N, ly W_XY/N, W_Y/N (precombined at plan creation: one table
-                       // value per element keeps all 16 loads of a thread in flight)
+  const T2 *kx, *ky;   // [nb][nxh][ny]: X leg (T or E) and Y leg (T or B)
+  const T *legT;       // [nlegs][nxh][ny] precombined tables (one table value per element keeps all the
+                       // loads of a thread in flight): TT {W_XY, ly W_XY, W_Y}/N; EB see eb_leg_tables_kernel
   const double *lx;
-  T2 *Lt;              // [nb][3][nxh][ny]
-  int ny, nxh, nb;
-  // leg factor (alpha + i beta) W: (0, lx) / (0, 1) with the ly-weighted table / (1, 0); no branch on the
-  // leg inside the element loop, so that the 32 loads of a thread are all issued before the first use
+  T2 *Lt;              // [nb][nlegs][nxh][ny]
+  int ny, nxh, nb, nlegs;
+  // leg factor (alpha + i beta) x table: kind 0 = i lx (x-gradient), 1 = i (y-gradient, ly is in the table),
+  // 2 = 1 (the Y leg); no branch on the leg inside the element loop
   struct Load {
     const T2 *k;
     const T *w;
@@ -292,14 +295,66 @@ struct LegsOps {
   __device__ __forceinline__ Load load(int ix, int plane) const {
     const int leg = plane / nb, m = plane - leg * nb;
     const size_t col = ((size_t)m * nxh + ix) * ny;
-    return Load{(leg == 2 ? ky : kx) + col, legT + ((size_t)leg * nxh + ix) * ny, leg == 2 ? 1.0 : 0.0,
-                leg == 0 ? lx[ix] : (leg == 1 ? 1.0 : 0.0)};
+    // TT: legs (x-grad, y-grad, Y);  EB: (x-grad re, x-grad im, y-grad re, y-grad im, Y re, Y im)
+    const int kind = nlegs == 3 ? leg : leg >> 1;
+    return Load{(kind == 2 ? ky : kx) + col, legT + ((size_t)leg * nxh + ix) * ny, kind == 2 ? 1.0 : 0.0,
+                kind == 0 ? lx[ix] : (kind == 1 ? 1.0 : 0.0)};
   }
   __device__ __forceinline__ Store store(int ix, int plane) const {
     const int leg = plane / nb, m = plane - leg * nb;
-    return Store{Lt + (((size_t)m * 3 + leg) * nxh + ix) * ny};
+    return Store{Lt + (((size_t)m * nlegs + leg) * nxh + ix) * ny};
   }
 };
+
+// EB on real fields.  With e^{2 i theta} = c + i s (theta = atan2(ly, lx)) the complex spin-2 fields of the
+// estimator split into real ones, each the inverse transform of a Hermitian array:
+//   g_x = IFFT(i lx E W_XY (c + i s)) = IFFT(i lx E W_XY c) + i IFFT(i lx E W_XY s),  same for g_y with ly,
+//   h   = IFFT(i B W_Y (c + i s))     = IFFT(-B W_Y s)      + i IFFT(B W_Y c),
+// and only Re(g conj h) = g_r h_r + g_i h_i survives the reference's ifft -> .real -> fft round trip
+// (the imaginary part of the product transforms to an anti-Hermitian term).  Tables, transposed layout:
+// {W_XY c, W_XY s, ly W_XY c, ly W_XY s, -W_Y s, W_Y c} / N
+template <typename T>
+__global__ void eb_leg_tables_kernel(const T *__restrict__ wxyT, const T *__restrict__ wyT, const double *__restrict__ ly,
+                                     const double *__restrict__ lx, int ny, int nxh, double invn, T *__restrict__ legT) {
+  const long long nh = (long long)ny * nxh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nh; i += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(i / ny), iy = (int)(i - (long long)ix * ny);
+    double c, s;
+    phase2(ly[iy], lx[ix], c, s);
+    const double wg = (double)wxyT[i] * invn, wh = (double)wyT[i] * invn;
+    legT[i] = (T)(wg * c);
+    legT[nh + i] = (T)(wg * s);
+    legT[2 * nh + i] = (T)(ly[iy] * wg * c);
+    legT[3 * nh + i] = (T)(ly[iy] * wg * s);
+    legT[4 * nh + i] = (T)(-wh * s);
+    legT[5 * nh + i] = (T)(wh * c);
+  }
+}
+
+// sum over a sample of pixels (every 16th row) of |k(p) - conj k(p')|^2 and |k(p)|^2: acc[0], acc[1]
+template <typename T2>
+__global__ void herm_check_kernel(const T2 *__restrict__ k, int ny, int nx, double *__restrict__ acc) {
+  const long long plane = blockIdx.y;
+  const T2 *kp = k + plane * (long long)ny * nx;
+  double d2 = 0.0, n2 = 0.0;
+  const int nrows = (ny + 15) / 16;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)nrows * nx; t += (long long)gridDim.x * blockDim.x) {
+    const int iy = (int)(t / nx) * 16, ix = (int)(t % nx);
+    const int my = iy ? ny - iy : 0, mx = ix ? nx - ix : 0;
+    const T2 a = kp[(long long)iy * nx + ix], b = kp[(long long)my * nx + mx];
+    const double dx = (double)a.x - (double)b.x, dy = (double)a.y + (double)b.y;
+    d2 += dx * dx + dy * dy;
+    n2 += (double)a.x * a.x + (double)a.y * a.y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(acc, d2);
+    atomicAdd(acc + 1, n2);
+  }
+}
 
 // legT[0] = W_XY/N, legT[1] = ly W_XY/N, legT[2] = W_Y/N in the transposed layout
 template <typename T>
@@ -410,7 +465,8 @@ __global__ void qe_finish_kernel(const T2 *__restrict__ Pk, const T *__restrict_
 }
 
 // row passes of the estimator: r2c of maps, c2r to maps, product with a second map -> r2c
-typedef oxk::RowModes<oxk::ROW_OUT_H, oxk::ROW_IN_H | oxk::ROW_OUT_MAP, oxk::ROW_WIN | oxk::ROW_OUT_H> QeRowModes;
+typedef oxk::RowModes<oxk::ROW_OUT_H, oxk::ROW_IN_H | oxk::ROW_OUT_MAP, oxk::ROW_WIN | oxk::ROW_OUT_H,
+                      oxk::ROW_WIN | oxk::ROW_WIN2 | oxk::ROW_OUT_H> QeRowModes;
 
 bool qe_fused_supported(int ny, int nx) {
   auto p2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
@@ -466,12 +522,13 @@ int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, i
     }
   }
   // ---- legs -> real fields -> products
-  OX_TRY(q->Lt.ensure(3 * hb));
-  OX_TRY(q->fields.ensure(sizeof(T) * (size_t)q->max_batch * 3 * n));
+  const int nl = q->nlegs;   // 3 (TT) or 6 (EB)
+  OX_TRY(q->Lt.ensure((size_t)nl * hb));
+  OX_TRY(q->fields.ensure(sizeof(T) * (size_t)q->max_batch * nl * n));
   OX_TRY(q->Pt.ensure(2 * hb));
   {
-    LegsOps<T> op{q->Kx.as<T2>(), two ? q->Ky.as<T2>() : q->Kx.as<T2>(), q->legT.as<T>(), lx, q->Lt.as<T2>(), ny, nxh, nb};
-    OX_COL_DISPATCH(T, +1, op, q->tw.p, q->tw_len, nxh, 3LL * nb, ny, st);               // Q2b
+    LegsOps<T> op{q->Kx.as<T2>(), two ? q->Ky.as<T2>() : q->Kx.as<T2>(), q->legT.as<T>(), lx, q->Lt.as<T2>(), ny, nxh, nb, nl};
+    OX_COL_DISPATCH(T, +1, op, q->tw.p, q->tw_len, nxh, (long long)nl * nb, ny, st);     // Q2b
     OX_TRY(st);
   }
   {
@@ -484,15 +541,24 @@ int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, i
     ra.tw = q->tw.as<T2>();
     ra.tw_len = q->tw_len;
     ra.ny = ny; ra.nx = nx; ra.mx = nx / 2;
-    OX_TRY(oxk::launch_row_any<T>(ra, 3LL * nb, QeRowModes()));                                        // Q3a
+    OX_TRY(oxk::launch_row_any<T>(ra, (long long)nl * nb, QeRowModes()));                              // Q3a
     ra.Hin = nullptr;
-    ra.map_in = q->fields.as<T>();
     ra.map_out = nullptr;
     ra.Hout = q->Pt.as<T2>();
-    ra.window = q->fields.as<T>() + 2 * n;   // the third field of each realisation
     ra.group = 2;
-    ra.map_in_group_stride = 3 * n;
-    ra.win_group_stride = 3 * n;
+    ra.map_in_group_stride = nl * n;
+    ra.win_group_stride = nl * n;
+    if (nl == 3) {
+      ra.map_in = q->fields.as<T>();           // g_x, g_y
+      ra.window = q->fields.as<T>() + 2 * n;   // x the third field of each realisation
+    } else {
+      // Re(g conj h) = g_r h_r + g_i h_i: fields (gx_r, gx_i, gy_r, gy_i, h_r, h_i)
+      ra.map_in = q->fields.as<T>();
+      ra.map_in2 = q->fields.as<T>() + n;
+      ra.map_in_sub_stride = 2 * n;
+      ra.window = q->fields.as<T>() + 4 * n;
+      ra.window2 = q->fields.as<T>() + 5 * n;
+    }
     OX_TRY(oxk::launch_row_any<T>(ra, 2LL * nb, QeRowModes()));                                        // Q3b
   }
   {
@@ -551,9 +617,31 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
   const long long n = (long long)ny * nx, nh = (long long)ny * nxh;
   const double invn = 1.0 / ((double)ny * (double)nx);
   const double *ly = g->ly.as<double>(), *lx = g->lx.as<double>();
-  if (q->fused) return reconstruct_fused_T<T, T2>(q, x, y, where, nb, already_ft, return_ft, accumulate, out, out_where);
   const bool two = (y != nullptr && y != x);
-  const long long plane = q->real_path ? nh : n;  // complex elements per staged k-map
+  // the half-plane paths need Hermitian Fourier inputs (transforms of real maps): verified on a sample of
+  // the pixels when the caller hands in k-maps; anything else goes through the reference's c2c chain
+  bool real = q->real_path && (q->est == OX_QE_TT || q->fused);
+  if (real && already_ft) {
+    OX_TRY(q->herm.ensure(2 * sizeof(double)));
+    OX_CUDA(cudaMemsetAsync(q->herm.p, 0, 2 * sizeof(double), g_stream));
+    const void *staged[2] = {nullptr, nullptr};
+    for (int leg = 0; leg < (two ? 2 : 1); leg++) {
+      OX_TRY(stage_in(leg ? y : x, where, sizeof(T2) * (size_t)nb * n, leg ? q->full2 : q->full, &staged[leg]));
+      herm_check_kernel<T2><<<dim3(sm_count(), nb), QT, 0, g_stream>>>((const T2 *)staged[leg], ny, nx, q->herm.as<double>());
+      OX_KERNEL_CHECK();
+    }
+    // host inputs are on the device now: hand the staged copies on instead of uploading them again
+    x = staged[0];
+    y = two ? staged[1] : (y ? staged[0] : nullptr);
+    where = OX_DEVICE;
+    double h[2];
+    OX_CUDA(cudaMemcpyAsync(h, q->herm.p, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    OX_CUDA(cudaStreamSynchronize(g_stream));
+    const double tol = q->dtype == OX_F64 ? 1e-20 : 1e-9;   // squared relative asymmetry
+    if (!(h[0] <= tol * h[1])) real = false;
+  }
+  if (real && q->fused) return reconstruct_fused_T<T, T2>(q, x, y, where, nb, already_ft, return_ft, accumulate, out, out_where);
+  const long long plane = real ? nh : n;  // complex elements per staged k-map
   OX_TRY(q->kx.ensure(sizeof(T2) * (size_t)q->max_batch * plane));
   if (two) OX_TRY(q->ky.ensure(sizeof(T2) * (size_t)q->max_batch * plane));
   // ---- inputs -> k-maps in the layout of the chosen path
@@ -563,7 +651,7 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
     if (already_ft) {
       const void *dsrc;
       OX_TRY(stage_in(src, where, sizeof(T2) * (size_t)nb * n, q->full, &dsrc));
-      if (q->real_path) {
+      if (real) {
         dim3 grid((unsigned)((nh + QT - 1) / QT), nb);
         full_to_half_kernel<T2><<<grid, QT, 0, g_stream>>>((const T2 *)dsrc, ny, nx, nxh, dstk);
         OX_KERNEL_CHECK();
@@ -574,7 +662,7 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
       OX_TRY(q->in_real.ensure(sizeof(T) * (size_t)q->max_batch * n));
       OX_CUDA(cudaMemcpyAsync(q->in_real.p, src, sizeof(T) * (size_t)nb * n,
                               where == OX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, g_stream));
-      if (q->real_path) {
+      if (real) {
         OX_TRY(q->fft.exec_r2c(nb, q->in_real.p, dstk));
       } else {
         OX_TRY(q->khat.ensure(sizeof(T2) * (size_t)q->max_batch * nh));
@@ -588,7 +676,7 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
   const T2 *kx = q->kx.as<T2>(), *ky = two ? q->ky.as<T2>() : kx;
   OX_TRY(q->khat.ensure(sizeof(T2) * (size_t)q->max_batch * nh));
   double2 *mf = accumulate ? q->mf.as<double2>() : nullptr;
-  if (q->real_path) {
+  if (real) {
     OX_TRY(q->legs.ensure(sizeof(T2) * (size_t)q->max_batch * 3 * nh));
     OX_TRY(q->fields.ensure(sizeof(T) * (size_t)q->max_batch * 3 * n));
     OX_TRY(q->prod.ensure(sizeof(T) * (size_t)q->max_batch * 2 * n));
@@ -608,9 +696,9 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
     OX_TRY(q->pk.ensure(sizeof(T2) * (size_t)q->max_batch * 2 * n));
     dim3 gf((unsigned)((n + QT - 1) / QT), nb);
     if (q->est == OX_QE_EB)
-      qe_gen_legs_kernel<T, T2, true><<<gf, QT, 0, g_stream>>>(kx, ky, q->wxy.as<T>(), q->wy.as<T>(), ly, lx, ny, nx, invn, q->legs.as<T2>());
+      qe_gen_legs_kernel<T, T2, true><<<gf, QT, 0, g_stream>>>(kx, ky, q->wxyF.as<T>(), q->wyF.as<T>(), ly, lx, ny, nx, invn, q->legs.as<T2>());
     else
-      qe_gen_legs_kernel<T, T2, false><<<gf, QT, 0, g_stream>>>(kx, ky, q->wxy.as<T>(), q->wy.as<T>(), ly, lx, ny, nx, invn, q->legs.as<T2>());
+      qe_gen_legs_kernel<T, T2, false><<<gf, QT, 0, g_stream>>>(kx, ky, q->wxyF.as<T>(), q->wyF.as<T>(), ly, lx, ny, nx, invn, q->legs.as<T2>());
     OX_KERNEL_CHECK();
     OX_TRY(q->fft.exec_c2c(3 * nb, q->legs.p, q->legs.p, CUFFT_INVERSE));
     qe_gen_prod_kernel<T2><<<gf, QT, 0, g_stream>>>(q->legs.as<T2>(), n, q->pk.as<T2>());
@@ -624,7 +712,7 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
         fullp = q->full.as<T2>();
       }
     }
-    qe_gen_div_kernel<T, T2><<<(unsigned)((nh + QT - 1) / QT), QT, 0, g_stream>>>(q->pk.as<T2>(), q->norm.as<T>(), ly, lx, ny, nx, nxh,
+    qe_gen_div_kernel<T, T2><<<(unsigned)((nh + QT - 1) / QT), QT, 0, g_stream>>>(q->pk.as<T2>(), q->normF.as<T>(), ly, lx, ny, nx, nxh,
                                                                                nb, q->khat.as<T2>(), fullp, mf);
     OX_KERNEL_CHECK();
     if (return_ft) {
@@ -680,10 +768,10 @@ int upload_tables(ox_qeplan *q, const double *wxy, const double *wy, const doubl
       OX_TRY(dst[t]->ensure(sizeof(T) * nh));
       table_half_kernel<T><<<(unsigned)((nh + QT - 1) / QT), QT, 0, g_stream>>>(fullT.as<T>(), g->ny, g->nx, g->nxh, dst[t]->as<T>());
       OX_KERNEL_CHECK();
-    } else {
-      OX_TRY(dst[t]->ensure(sizeof(T) * n));
-      OX_CUDA(cudaMemcpyAsync(dst[t]->p, fullT.p, sizeof(T) * n, cudaMemcpyDeviceToDevice, g_stream));
     }
+    DevBuf *dstF[3] = {&q->wxyF, &q->wyF, &q->normF};
+    OX_TRY(dstF[t]->ensure(sizeof(T) * n));
+    OX_CUDA(cudaMemcpyAsync(dstF[t]->p, fullT.p, sizeof(T) * n, cudaMemcpyDeviceToDevice, g_stream));
     OX_CUDA(cudaStreamSynchronize(g_stream));
   }
   return OX_OK;
@@ -693,9 +781,15 @@ template <typename T>
 int make_leg_tables(ox_qeplan *q) {
   ox_geometry *g = q->g;
   const long long nh = (long long)g->ny * g->nxh;
-  OX_TRY(q->legT.ensure(sizeof(T) * 3 * nh));
-  leg_tables_kernel<T><<<sm_count() * 8, QT, 0, g_stream>>>(q->wxyT.as<T>(), q->wyT.as<T>(), g->ly.as<double>(), g->ny, g->nxh,
-                                                            1.0 / ((double)g->ny * (double)g->nx), q->legT.as<T>());
+  const double invn = 1.0 / ((double)g->ny * (double)g->nx);
+  q->nlegs = q->est == OX_QE_EB ? 6 : 3;
+  OX_TRY(q->legT.ensure(sizeof(T) * (size_t)q->nlegs * nh));
+  if (q->est == OX_QE_EB)
+    eb_leg_tables_kernel<T><<<sm_count() * 8, QT, 0, g_stream>>>(q->wxyT.as<T>(), q->wyT.as<T>(), g->ly.as<double>(),
+                                                                 g->lx.as<double>(), g->ny, g->nxh, invn, q->legT.as<T>());
+  else
+    leg_tables_kernel<T><<<sm_count() * 8, QT, 0, g_stream>>>(q->wxyT.as<T>(), q->wyT.as<T>(), g->ly.as<double>(), g->ny, g->nxh,
+                                                              invn, q->legT.as<T>());
   OX_KERNEL_CHECK();
   OX_CUDA(cudaStreamSynchronize(g_stream));
   q->wxyT.release();
@@ -713,7 +807,6 @@ int ox_qeplan_create(ox_geometry *g, int est, const double *wxy, const double *w
   OX_REQUIRE(est == OX_QE_TT || est == OX_QE_EB, "unknown estimator %d", est);
   OX_REQUIRE(dtype == OX_F64 || dtype == OX_F32, "bad dtype %d", dtype);
   OX_REQUIRE(max_batch >= 1, "max_batch must be >= 1");
-  OX_REQUIRE(!(real_path && est != OX_QE_TT), "the half-plane path is for TT only");
   ox_qeplan *q = new ox_qeplan;
   q->g = g;
   q->est = est;
@@ -758,7 +851,11 @@ int ox_qe_meanfield_reset(ox_qeplan *q) {
   return OX_OK;
 }
 
-int ox_qe_path(ox_qeplan *q) { return q ? (q->fused ? 2 : (q->real_path ? 1 : 0)) : -1; }
+int ox_qe_path(ox_qeplan *q) {
+  if (!q) return -1;
+  if (q->fused) return q->est == OX_QE_EB ? 3 : 2;
+  return (q->real_path && q->est == OX_QE_TT) ? 1 : 0;
+}
 
 int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem) {
   OX_REQUIRE(q, "null plan");

@@ -150,8 +150,11 @@ class qest(object):
         wy = np.ascontiguousarray(N.WY(XY[1] + XY[1]), dtype=np.float64)
         norm = np.ascontiguousarray(_fmask(np.nan_to_num(AL), N.fmaskK), dtype=np.float64)
         ny, nx = self.geometry.shape
-        real_path = (XY == 'TT' and _symmetric(wxy) and _symmetric(wy) and _symmetric(norm, 1e-12)
-                     and (ny % 2 or not wxy[ny // 2].any()) and (nx % 2 or not wxy[:, nx // 2].any()))
+        # symmetric filters that vanish on the Nyquist row/column: Hermitian inputs (transforms of real maps)
+        # give real fields, so TT -- and EB, split into real and imaginary parts -- run on half planes
+        real_path = (_symmetric(wxy) and _symmetric(wy) and _symmetric(norm, 1e-12)
+                     and (ny % 2 or not (wxy[ny // 2].any() or wy[ny // 2].any()))
+                     and (nx % 2 or not (wxy[:, nx // 2].any() or wy[:, nx // 2].any())))
         h = C.c_void_p()
         est = _capi.QE_TT if XY == 'TT' else _capi.QE_EB
         check(lib.ox_qeplan_create(self.geometry.handle, est, ptr(wxy), ptr(wy), ptr(norm), OX_HOST, self.dtype,
@@ -159,11 +162,12 @@ class qest(object):
         self._plans[XY] = (h, real_path)
 
     def path(self, XY):
-        """Implementation behind estimator XY: 'c2c' (full-plane chain on cuFFT), 'half' (TT on half
-        planes, cuFFT) or 'fused' (TT on half planes, hand-written FFT passes; include/orphx.h ox_qe_path)."""
+        """Implementation behind estimator XY for Hermitian inputs: 'c2c' (full-plane chain on cuFFT), 'half' (TT
+        on half planes, cuFFT), 'fused' (TT) / 'fused_eb' (EB) on half planes with the hand-written FFT passes
+        (include/orphx.h ox_qe_path).  k-maps that are not Hermitian always take the c2c chain."""
         if XY not in self._plans:
             self._make_plan(XY)
-        return {0: 'c2c', 1: 'half', 2: 'fused'}[lib.ox_qe_path(self._plans[XY][0])]
+        return {0: 'c2c', 1: 'half', 2: 'fused', 3: 'fused_eb'}[lib.ox_qe_path(self._plans[XY][0])]
 
     def _run(self, XY, X, Y, alreadyFTed, returnFt, accumulate):
         if XY not in self._plans:

@@ -74,9 +74,11 @@ def test_tt_kappa_matches_oracle(masked, npix, path, theory):
     assert relerr(kb2, np.stack([qo.kappa_from_map("TT", m) for m in stack])) < TOL64
 
 
-def test_eb_kappa_matches_oracle(theory):
+@pytest.mark.parametrize("npix,path", [(128, "c2c"), (512, "fused_eb")])
+def test_eb_kappa_matches_oracle(npix, path, theory):
     from orphics_b200 import maps
-    shape, wcs, so, wo, q, qo = setup(128, 2.0, theory, True)
+    shape, wcs, so, wo, q, qo = setup(npix, 2.0, theory, True)
+    assert q.path("EB") == path
     qo.N.AL["EB"] = np.asarray(q.N.AL["EB"])
     rng = np.random.RandomState(4)
     iqu = rng.standard_normal((3,) + shape) * np.array([50., 3., 3.])[:, None, None]
@@ -92,6 +94,25 @@ def test_eb_kappa_matches_oracle(theory):
     assert relerr(kf, qo.kappa_from_map("EB", ktebo[0], ktebo[1], ktebo[2], alreadyFTed=True, returnFt=True)) < TOL64
     E, B = rng.standard_normal((2,) + shape)
     assert relerr(q.kappa_from_map("EB", None, E, B), qo.kappa_from_map("EB", None, E, B)) < TOL64     # real E/B maps in
+    # k-maps that are NOT Hermitian (transforms of complex fields) must take the reference's c2c chain on every path
+    kE = np.fft.fft2(rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+    kB = np.fft.fft2(rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+    got = q.kappa_from_map("EB", None, kE, kB, alreadyFTed=True, returnFt=True)
+    assert relerr(got, qo.kappa_from_map("EB", None, kE, kB, alreadyFTed=True, returnFt=True)) < TOL64
+    gotT = q.kappa_from_map("TT", kE, alreadyFTed=True, returnFt=True)
+    qo.N.AL["TT"] = np.asarray(q.N.AL["TT"])
+    assert relerr(gotT, qo.kappa_from_map("TT", kE, alreadyFTed=True, returnFt=True)) < TOL64
+    # batches with the mean-field stack
+    Es, Bs = rng.standard_normal((2, 3) + shape)
+    q.reset_meanfield("EB")
+    kb = q.kappa_from_maps("EB", Es, Bs, returnFt=True, accumulate_meanfield=True)
+    want = np.stack([qo.kappa_from_map("EB", None, e, b, returnFt=True) for e, b in zip(Es, Bs)])
+    assert relerr(kb, want) < TOL64
+    acc, cnt = q.meanfield("EB")
+    iy, ix = (-np.arange(shape[0])) % shape[0], (-np.arange(shape[1])) % shape[1]
+    tot = want.sum(0)
+    herm = 0.5 * (tot + np.conj(tot[iy][:, ix]))
+    assert cnt == 3 and relerr(acc, herm[:, :shape[1] // 2 + 1]) < TOL64
 
 
 def test_tt_fused_equals_cufft_rectangular(theory, monkeypatch):

@@ -35,7 +35,7 @@ tmask = maps.mask_kspace(shape, wcs, lmin=300, lmax=2000)
 kmask = maps.mask_kspace(shape, wcs, lmin=20, lmax=3500)
 q = lensing.qest(shape, wcs, th, noise2d=n2d, beam2d=beam, kmask=tmask, kmask_P=tmask, kmask_K=kmask, pol=(est == "EB"),
                  unlensed_equals_lensed=True, dtype=rdt, max_batch=nb)
-h, real_path = q._plans[est]
+h = q._plans[est][0]
 rng = np.random.RandomState(0)
 N = npix * npix
 if est == "TT":
@@ -43,10 +43,11 @@ if est == "TT":
     y = None
     already = 0
 else:
-    mk = lambda: (rng.standard_normal((nb, npix, npix)) + 1j * rng.standard_normal((nb, npix, npix))).astype(cdt)
-    x = _capi.DeviceBuffer(nb * N * 2 * s).upload(mk())
-    y = _capi.DeviceBuffer(nb * N * 2 * s).upload(mk())
-    already = 1
+    # real E and B maps in HBM (their transforms are Hermitian, as those of iqu2teb are); the SURVEY 8d
+    # accounting (76 s N) includes the two input transforms
+    x = _capi.DeviceBuffer(nb * N * s).upload((rng.standard_normal((nb, npix, npix)) * 3).astype(rdt))
+    y = _capi.DeviceBuffer(nb * N * s).upload((rng.standard_normal((nb, npix, npix)) * 3).astype(rdt))
+    already = 0
 out = _capi.DeviceBuffer(nb * N * 2 * s)
 
 

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <random>
 #include "ox_rng_tables.h"
@@ -51,10 +52,11 @@ static void bm(uint32_t xx, uint32_t xy, uint32_t xz, uint32_t xw, double &n1, d
   si = hilo(hiint(si) ^ (int)((q & 2u) << 30), loint(si));
   n1 = g * co; n2 = g * si;
 }
-int main() {
+int main(int argc, char **argv) {
+  const long niter = argc > 1 ? atol(argv[1]) : 20000000;
   std::mt19937_64 gen(12345);
   double worst_n = 0, worst_L = 0;
-  for (long it = 0; it < 20000000; it++) {
+  for (long it = 0; it < niter; it++) {
     uint64_t a = gen(), b = gen();
     if (it < 64) a = ~0ull << (it);                 // u1 near 1 ... small
     if (it >= 64 && it < 128) a = (1ull << (it - 64)) - 1; // tiny u1
