@@ -140,9 +140,9 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
   } else if (MODE == OX_NOISE_PHILOX) {
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      oxrng::box_muller_fast(oxrng::philox4x32_10(make_uint4(p, 0u, c, 0u), keys), logtab, pr[c], pi[c]);
+      oxrng::box_muller<T>(oxrng::philox4x32_10(make_uint4(p, 0u, c, 0u), keys), logtab, pr[c], pi[c]);
       // (the self-conjugate pixels draw twice: same counter, same value)
-      oxrng::box_muller_fast(oxrng::philox4x32_10(make_uint4(q, 0u, c, 0u), keys), logtab, qr[c], qi[c]);
+      oxrng::box_muller<T>(oxrng::philox4x32_10(make_uint4(q, 0u, c, 0u), keys), logtab, qr[c], qi[c]);
     }
   } else {
     const bool conj_me = INTERIOR ? iy > (a.ny >> 1) : q < p, selfc = INTERIOR ? false : q == p;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       double n1, n2;
-      oxrng::box_muller_fast(oxrng::philox4x32_10(make_uint4(canon, 0u, c, 1u), keys), logtab, n1, n2);
+      oxrng::box_muller<T>(oxrng::philox4x32_10(make_uint4(canon, 0u, c, 1u), keys), logtab, n1, n2);
       pr[c] = selfc ? n1 : n1 * 0.70710678118654752440;
       pi[c] = selfc ? 0.0 : (conj_me ? -n2 : n2) * 0.70710678118654752440;
       qr[c] = pr[c];

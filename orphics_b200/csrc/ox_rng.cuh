@@ -117,4 +117,52 @@ __device__ __forceinline__ void box_muller_fast(uint4 x, const double2 *__restri
   n2 = g * si;
 }
 
+// Single-precision variant for the float32 pipeline (tolerance 1e-5): the same random bits and the same
+// table-based reduction of u1 (two fp64 operations keep the relative accuracy of -2 ln u1 as u1 -> 1), then
+// the series, the square root and the sine/cosine polynomials in fp32 -- the fp64 pipe, which bounds the
+// double-precision version, is almost idle here.  Normals agree with the fp64 definition to ~3e-7.
+__device__ __forceinline__ void box_muller_fast_f32(uint4 x, const double2 *__restrict__ tab, double &n1, double &n2) {
+  const unsigned long long n = ((((unsigned long long)x.x << 32) | x.y) >> 11) + 1ull;
+  const double d = (double)n;
+  const int hi = __double2hiint(d);
+  const unsigned mant = (unsigned)hi & 0xfffffu;
+  const double m = __hiloint2double((int)(mant | 0x3ff00000u), __double2loint(d));
+  const double2 t = tab[(mant + 0x1000u) >> 13];
+  const float w = (float)fma(m, t.x, 2.0);
+  const float ed = (float)((hi >> 20) - (1023 + 53));
+  const float base = fmaf(ed, (float)OX_RNG_NEG2LN2, (float)t.y);  // cancels exactly for u1 in [1/2 (1 + 255/256), 1)
+  const float L = base + fmaf(fmaf(w, 1.0f / 12.0f, 0.25f), w * w, w);
+  const float g = __fsqrt_rn(L);
+  const unsigned kb_hi = x.z >> 11, kb_lo = (x.w >> 11) | (x.z << 21);
+  const unsigned q = (kb_hi + (1u << 18)) >> 19;
+  const int r_hi = (int)kb_hi - (int)(q << 19);
+  const long long ri = (long long)(((unsigned long long)(unsigned)r_hi << 32) | kb_lo);
+  const float tt = (float)ri * 0x1p-53f;  // |tt| <= 1/8 turn
+  const float z = tt * tt;
+  // Taylor coefficients of sin(2 pi t)/t and cos(2 pi t) in t^2: truncation 2e-9 / 3e-8 at |t| = 1/8
+  constexpr float S0 = 6.283185307179586f, S1 = -41.341702240399755f, S2 = 81.60524927607504f, S3 = -76.70585975306136f,
+                  S4 = 42.05869394489765f;
+  constexpr float C1 = -19.739208802178716f, C2 = 64.93939402266829f, C3 = -85.45681720669373f, C4 = 60.24464137187666f;
+  float sn = fmaf(S4, z, S3), cs = fmaf(C4, z, C3);
+  sn = fmaf(sn, z, S2);
+  cs = fmaf(cs, z, C2);
+  sn = fmaf(sn, z, S1);
+  cs = fmaf(cs, z, C1);
+  sn = fmaf(sn, z, S0) * tt;
+  cs = fmaf(cs, z, 1.0f);
+  const bool swap = q & 1u;
+  float co = swap ? sn : cs, si = swap ? cs : sn;
+  co = __int_as_float(__float_as_int(co) ^ (int)(((q + 1u) & 2u) << 30));
+  si = __int_as_float(__float_as_int(si) ^ (int)((q & 2u) << 30));
+  n1 = (double)(g * co);
+  n2 = (double)(g * si);
+}
+
+// dispatch on the pipeline's real type
+template <typename T>
+__device__ __forceinline__ void box_muller(uint4 x, const double2 *__restrict__ tab, double &n1, double &n2) {
+  if (sizeof(T) == 4) box_muller_fast_f32(x, tab, n1, n2);
+  else box_muller_fast(x, tab, n1, n2);
+}
+
 }  // namespace oxrng

@@ -334,3 +334,30 @@ def test_fused_and_cufft_paths_agree_at_2048(monkeypatch):
         for s, (i, j) in enumerate(pairs):
             scale = np.sqrt(np.abs(c[:, auto[i]] * c[:, auto[j]]))
             assert np.max(np.abs(a[:, s] - c[:, s]) / scale) < TOL64
+
+
+@pytest.mark.parametrize("pol", [False, True])
+def test_fp32_fused_pipeline_philox_within_1e5(pol, theory):
+    """float32 mode on the hand-written kernels (single-precision Box-Muller, FFTs and binning) against the
+    fp64 definition of the noise pushed through the restated reference algorithm: maps and bandpowers 1e-5."""
+    from orphics_b200 import maps, stats
+    npix = 512
+    shape, wcs, so, wo, modl, ps = setup(npix, 2.0, pol, theory)
+    edges = np.arange(200, 2600, 100.0)
+    og, ofc, ob = omaps.MapGen(so, wo, ps), omaps.FourierCalc(so, wo), ostats.bin2D(modl, edges)
+    mg = maps.MapGen(shape, wcs, covsqrt=np.asarray(og.covsqrt), noise="philox_hermitian", dtype=np.float32, max_batch=2)
+    fc = maps.FourierCalc(shape, wcs, dtype=np.float32, max_batch=2)
+    b = stats.bin2D(fc.geometry.modlmap(), edges, geometry=fc.geometry)
+    pipe = maps.SimPipeline(mg, fc, b)
+    assert pipe.path == "fused"
+    bp = pipe.run([1000, 1001], keep_maps=True)
+    last = pipe.last_maps(2)
+    for i, s in enumerate((1000, 1001)):
+        rand = philox_np.noise_field(s, 3 if pol else 1, npix, npix, hermitian=True)
+        mo = og.map_from_noise(oenmap.ndmap(rand if pol else rand[0], wo))
+        got = last[i] if pol else last[i, 0]
+        assert got.dtype == np.float32
+        assert relerr(got, mo) < TOL32
+        p2o = ofc.power2d(mo)[0]
+        want = ob.bin(p2o[0, 0] if pol else p2o)[1]
+        assert np.max(np.abs(bp[i, 0] - want) / np.max(np.abs(want))) < TOL32
