@@ -36,6 +36,9 @@ using namespace oxk;
 #ifndef OX_KA_REGS
 #define OX_KA_REGS 0   // register cap per thread asked of K_A (T-only), 0 = none
 #endif
+#ifndef OX_KA_ROLLED
+#define OX_KA_ROLLED 4   // unroll factor of the noise loop of K_A (0 = 16 pixels straight-line into registers)
+#endif
 #ifndef OX_KC_REGS
 #define OX_KC_REGS 128   // register cap per thread asked of K_C (T-only), 0 = none
 #endif
@@ -254,6 +257,33 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
     sim_pixel<T, NC, MODE, PATH>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);      \
     v[m] = z[0];                                                                              \
   }
+#if OX_KA_ROLLED
+    // The 16 values are generated four at a time in a rolled loop and parked in the thread's OWN shared-memory
+    // slots (u + m*NT are exactly the inputs of its first butterfly, so no barrier is needed before reading
+    // them back).  Generating all 16 straight-line into registers (OX_KA_ROLLED=0) costs 186 registers and
+    // 54 KB of instructions per warp with no reuse: ncu showed 0.3 warps per issue stalled on instruction
+    // fetch; the rolled loop is 12% faster (profiles/r01_variants.txt).
+    {
+      constexpr int UR = OX_KA_ROLLED;
+#define OX_ROLL16(PATH)                                                                       \
+  _Pragma("unroll UR") for (int m = 0; m < 16; m++) {                                         \
+    T2 z[NC];                                                                                 \
+    sim_pixel<T, NC, MODE, PATH>(a, keys, logtab, noise_sim, ix, mxp, u + m * NT, h, z);      \
+    s[pad(u + m * NT)] = z[0];                                                                \
+  }
+      if (interior && a.cov_symmetric && MODE == OX_NOISE_PHILOX_HERMITIAN) {
+        OX_ROLL16(2)
+      } else if (interior) {
+        OX_ROLL16(1)
+      } else {
+        OX_ROLL16(0)
+      }
+#undef OX_ROLL16
+      SmemLoad<T2> lds{s};
+      FFT::template run<+1, true, false>(s, tws, u, 0, lds, st);
+      return;
+    }
+#endif
     if (interior && a.cov_symmetric && MODE == OX_NOISE_PHILOX_HERMITIAN) {
       OX_GEN16(2)
     } else if (interior) {
