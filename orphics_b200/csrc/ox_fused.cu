@@ -34,7 +34,7 @@ using namespace oxk;
 
 // compile-time tuning knobs (defaults = the measured best on B200, profiles/r01_variants.txt)
 #ifndef OX_KA_REGS
-#define OX_KA_REGS 0   // register cap per thread asked of K_A (T-only), 0 = none
+#define OX_KA_REGS 100 // register cap per thread asked of K_A (T-only), 0 = none: 100 -> five CTAs of 128 threads per SM
 #endif
 #ifndef OX_KA_ROLLED
 #define OX_KA_ROLLED 4   // unroll factor of the noise loop of K_A (0 = 16 pixels straight-line into registers)
@@ -221,7 +221,7 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
 }
 
 template <typename T, int LY, int NC, int MODE>
-__global__ void __launch_bounds__(NC *(LY / 16), (NC == 1 ? minb_for(LY / 16, OX_KA_REGS) : 1))
+__global__ void __launch_bounds__(NC *(LY / 16), (NC == 1 && LY == 2048 ? minb_for(LY / 16, OX_KA_REGS) : 1))  // (the cap spills at other lengths)
 fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[nsim][NC][mx+1][ny]*/) {
   typedef typename V2<T>::type T2;
   typedef BlockFFT<T, LY> FFT;
@@ -505,7 +505,7 @@ int launch_sim_col_mode(SimColArgs<T> &a, void *Ht, int nsim) {
   size_t smem = sizeof(T2) * NC * padded_size(LY) + sizeof(double2) * oxrng::LOG_TABLE_ENTRIES;
   OX_REQUIRE(smem <= SMEM_MAX, "fused sim: column of %d x %d comps needs %zu B of shared memory", LY, NC, smem);
   auto k = fused_sim_col_kernel<T, LY, NC, MODE>;
-  OX_TRY(set_smem(k, smem));
+  OX_TRY(set_smem(k, smem, NC == 1));
   dim3 grid(a.mx + 1, nsim);
   k<<<grid, NC * (LY / 16), smem, g_stream>>>(a, (T2 *)Ht);
   OX_KERNEL_CHECK();

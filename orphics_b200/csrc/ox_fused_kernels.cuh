@@ -51,9 +51,15 @@ struct GlobalLoad {
   __device__ __forceinline__ T2 operator()(int e, int) const { return src[e]; }
 };
 
+// max_carveout: ask for the largest shared-memory carve-out so that occupancy is set by the registers.  Only
+// for kernels that do not lean on L1 for their global loads: K_A gains 6% with five 37 KB CTAs per SM, while the
+// row kernel and K_C (window / slot-index / twiddle loads through L1) lose 3% and 30% with it
+// (profiles/r01_variants.txt)
 template <typename F>
-int set_smem(F kernel, size_t bytes) {
+int set_smem(F kernel, size_t bytes, bool max_carveout = false) {
   if (bytes > 48 * 1024) OX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (max_carveout)
+    OX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   return OX_OK;
 }
 
