@@ -11,6 +11,9 @@
 #ifndef OX_KB_ROWS64
 #define OX_KB_ROWS64 4  // rows per CTA of the row kernel for 16-byte elements (64 B segments)
 #endif
+#ifndef OX_KB_MINSEG
+#define OX_KB_MINSEG 32 // smallest contiguous segment (bytes) of the transposed layout a row tile may touch
+#endif
 #ifndef OX_KB_MINB
 #define OX_KB_MINB 2    // resident CTAs per SM asked of the row kernel (CTAs of <= 256 threads)
 #endif
@@ -279,10 +282,10 @@ template <typename T, int MX>
 struct RowCfg {
   typedef typename V2<T>::type T2;
   static constexpr int WANT = sizeof(T2) == 16 ? OX_KB_ROWS64 : 8;
-  static constexpr int MINR = (int)(32 / sizeof(T2));
+  static constexpr int MINR = (int)(OX_KB_MINSEG / sizeof(T2)) > 0 ? (int)(OX_KB_MINSEG / sizeof(T2)) : 1;
   static constexpr size_t ROW = sizeof(T2) * padded_size(MX);
   static constexpr int FIT = (int)((SMEM_MAX / 2) / ROW);  // rows per CTA that leave room for a second CTA
-  static constexpr int R = FIT >= WANT ? WANT : (FIT >= MINR ? (FIT >= 4 ? 4 : 2) : MINR);
+  static constexpr int R = FIT >= WANT ? WANT : (FIT >= MINR ? (FIT >= 4 ? 4 : (FIT >= 2 ? 2 : 1)) : MINR);
 };
 
 template <typename T, int MX, int MODE>
