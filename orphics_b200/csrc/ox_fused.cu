@@ -36,6 +36,12 @@ using namespace oxk;
 #ifndef OX_KA_REGS
 #define OX_KA_REGS 100 // register cap per thread asked of K_A (T-only), 0 = none: 100 -> five CTAs of 128 threads per SM
 #endif
+#ifndef OX_KA3_SEQ
+#define OX_KA3_SEQ 0    // three-component K_A: 1 = one CTA of LY/16 threads transforms the components one after the other
+#endif
+#ifndef OX_KA3_MINB
+#define OX_KA3_MINB 1   // resident CTAs per SM asked of the three-component K_A (384 threads)
+#endif
 #ifndef OX_KA_ROLLED
 #define OX_KA_ROLLED 4   // unroll factor of the noise loop of K_A (0 = 16 pixels straight-line into registers)
 #endif
@@ -49,6 +55,7 @@ using namespace oxk;
 namespace {
 
 // min resident CTAs per SM that caps the registers per thread at `regs` (0 = no cap)
+__host__ __device__ constexpr int ka_threads(int nc, int ly) { return (nc > 1 && OX_KA3_SEQ) ? ly / 16 : nc * (ly / 16); }
 constexpr int minb_for(int threads, int regs) { return regs > 0 && 65536 / (threads * regs) > 1 ? 65536 / (threads * regs) : 1; }
 
 // ---- shared helpers -------------------------------------------------------------------
@@ -221,11 +228,11 @@ __device__ __forceinline__ void sim_pixel(const SimColArgs<T> &a, const oxrng::P
 }
 
 template <typename T, int LY, int NC, int MODE>
-__global__ void __launch_bounds__(NC *(LY / 16), (NC == 1 && LY == 2048 ? minb_for(LY / 16, OX_KA_REGS) : 1))  // (the cap spills at other lengths)
+__global__ void __launch_bounds__(ka_threads(NC, LY), (NC == 1 ? (LY == 2048 ? minb_for(LY / 16, OX_KA_REGS) : 1) : (LY == 2048 ? OX_KA3_MINB : 1)))  // (the caps spill at other lengths)
 fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[nsim][NC][mx+1][ny]*/) {
   typedef typename V2<T>::type T2;
   typedef BlockFFT<T, LY> FFT;
-  constexpr int NT = FFT::NT, NTHREADS = NC * NT, PS = padded_size(LY);
+  constexpr int NT = FFT::NT, NTHREADS = ka_threads(NC, LY), PS = padded_size(LY);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T2 *s = reinterpret_cast<T2 *>(smem_raw);                                        // [NC][PS]
   double2 *logtab = reinterpret_cast<double2 *>(smem_raw + sizeof(T2) * NC * PS);  // [129]
@@ -294,6 +301,25 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
 #undef OX_GEN16
     RegLoad<T2> ld{v};
     FFT::template run<+1, false, false>(s, tws, u, 0, ld, st);
+  } else if (OX_KA3_SEQ) {
+    // experiment: LY/16 threads generate all components of their 16 pixels into their own slots of the NC
+    // buffers, then transform the components one after the other
+    const bool fast = ix != 0 && ix != a.mx && a.cov_symmetric && MODE == OX_NOISE_PHILOX_HERMITIAN;
+#pragma unroll 2
+    for (int m = 0; m < 16; m++) {
+      T2 z[NC];
+      if (fast) sim_pixel<T, NC, MODE, 2>(a, keys, logtab, noise_sim, ix, mxp, tid + m * NT, h, z);
+      else sim_pixel<T, NC, MODE, 0>(a, keys, logtab, noise_sim, ix, mxp, tid + m * NT, h, z);
+#pragma unroll
+      for (int c = 0; c < NC; c++) s[c * PS + pad(tid + m * NT)] = z[c];
+    }
+    typename FFT::Twiddles tw2;
+    tw2.init(a.tw, a.tw_len / LY, tid);
+    for (int c = 0; c < NC; c++) {
+      SmemLoad<T2> ld{s + c * PS};
+      GlobalStore<T2> stc{Ht + (((size_t)sim * NC + c) * (a.mx + 1) + ix) * a.ny};
+      FFT::template run<+1, true, false>(s + c * PS, tw2, tid, 0, ld, stc);
+    }
   } else {
     if (ix != 0 && ix != a.mx && a.cov_symmetric && MODE == OX_NOISE_PHILOX_HERMITIAN) {
 #pragma unroll 2
@@ -505,9 +531,9 @@ int launch_sim_col_mode(SimColArgs<T> &a, void *Ht, int nsim) {
   size_t smem = sizeof(T2) * NC * padded_size(LY) + sizeof(double2) * oxrng::LOG_TABLE_ENTRIES;
   OX_REQUIRE(smem <= SMEM_MAX, "fused sim: column of %d x %d comps needs %zu B of shared memory", LY, NC, smem);
   auto k = fused_sim_col_kernel<T, LY, NC, MODE>;
-  OX_TRY(set_smem(k, smem, NC == 1));
+  OX_TRY(set_smem(k, smem, NC == 1 || OX_KA3_MINB > 1));
   dim3 grid(a.mx + 1, nsim);
-  k<<<grid, NC * (LY / 16), smem, g_stream>>>(a, (T2 *)Ht);
+  k<<<grid, ka_threads(NC, LY), smem, g_stream>>>(a, (T2 *)Ht);
   OX_KERNEL_CHECK();
   return OX_OK;
 }
