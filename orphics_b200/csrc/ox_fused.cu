@@ -40,7 +40,8 @@ using namespace oxk;
 #define OX_KA3_SEQ 0    // three-component K_A: 1 = one CTA of LY/16 threads transforms the components one after the other
 #endif
 #ifndef OX_KA3_MINB
-#define OX_KA3_MINB 1   // resident CTAs per SM asked of the three-component K_A (384 threads)
+#define OX_KA3_MINB 2   // resident CTAs per SM asked of the three-component K_A (384 threads): 2 -> 80 registers, the
+                        // 136 B of spills cost less than a lone CTA whose noise and FFT phases cannot overlap
 #endif
 #ifndef OX_KA_ROLLED
 #define OX_KA_ROLLED 4   // unroll factor of the noise loop of K_A (0 = 16 pixels straight-line into registers)
