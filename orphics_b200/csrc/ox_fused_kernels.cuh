@@ -14,6 +14,9 @@
 #ifndef OX_KB_MINSEG
 #define OX_KB_MINSEG 32 // smallest contiguous segment (bytes) of the transposed layout a row tile may touch
 #endif
+#ifndef OX_KB_MINB_C2R
+#define OX_KB_MINB_C2R 2 // the same for the c2r-only row pass (no forward transform: fewer live registers)
+#endif
 #ifndef OX_KB_MINB
 #define OX_KB_MINB 2    // resident CTAs per SM asked of the row kernel (CTAs of <= 256 threads)
 #endif
@@ -165,7 +168,7 @@ enum { ROW_IN_H = 1, ROW_OUT_MAP = 2, ROW_WIN = 4, ROW_OUT_H = 8, ROW_WIN2 = 16 
 
 // R rows per CTA, each a length-MX complex FFT handled by NT = MX/16 threads
 template <typename T, int MX, int R, int MODE>
-__global__ void __launch_bounds__(R *(MX / 16), (R * (MX / 16) <= 256 ? OX_KB_MINB : 1))
+__global__ void __launch_bounds__(R *(MX / 16), (R * (MX / 16) <= 256 ? ((MODE & ROW_OUT_H) ? OX_KB_MINB : OX_KB_MINB_C2R) : 1))
 fused_row_kernel(RowArgs<T> a) {
   constexpr bool IN_H = MODE & ROW_IN_H, OUT_MAP = MODE & ROW_OUT_MAP, WIN = MODE & ROW_WIN, OUT_H = MODE & ROW_OUT_H;
   constexpr bool WIN2 = MODE & ROW_WIN2;
