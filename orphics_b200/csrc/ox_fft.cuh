@@ -21,7 +21,17 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 namespace oxfft {
+
+// A last-stage StoreOp may declare `static constexpr bool PREFETCH = true` and provide pre(m) (start the global
+// loads it needs for output m) and use(f, v, m) (consume output m with the prefetched operands): the engine then
+// issues the loads of butterfly q+1 while butterfly q is being stored, instead of one exposed latency per element.
+template <class S, class = void>
+struct has_prefetch : std::false_type {};
+template <class S>
+struct has_prefetch<S, std::void_t<decltype(S::PREFETCH)>> : std::integral_constant<bool, S::PREFETCH> {};
 
 template <typename T>
 struct V2;
@@ -270,7 +280,12 @@ struct BlockFFT {
   static __device__ __forceinline__ void stage(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
                                                const StoreOp &st) {
     constexpr int Q = 16 / R;
+    constexpr bool PF = LAST && Q > 1 && has_prefetch<StoreOp>::value;
     T2 v[16];
+    if constexpr (PF) {
+#pragma unroll
+      for (int r = 0; r < R; r++) st.pre(r * Q);  // operands of the first butterfly's outputs
+    }
 #pragma unroll
     for (int q = 0; q < Q; q++) {
 #pragma unroll
@@ -290,10 +305,17 @@ struct BlockFFT {
       const int j = u + q * NT;
       const int k = j & (Ns - 1);
       const int d = (j - k) * R + k;
+      if constexpr (PF) {
+        if (q + 1 < Q) {
+#pragma unroll
+          for (int r = 0; r < R; r++) st.pre(q + 1 + r * Q);
+        }
+      }
 #pragma unroll
       for (int r = 0; r < R; r++) {
         const T2 val = v[q * R + (R == 16 ? out16(r) : r)];
-        if (LAST) st(d + r * Ns, val, q + r * Q);  // here Ns = L/R, so d + r*Ns = u + (q + r*Q)*NT
+        if constexpr (PF) st.use(d + r * Ns, val, q + r * Q);
+        else if (LAST) st(d + r * Ns, val, q + r * Q);  // here Ns = L/R, so d + r*Ns = u + (q + r*Q)*NT
         else s[pad(d + r * Ns)] = val;
       }
     }

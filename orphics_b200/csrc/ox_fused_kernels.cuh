@@ -14,6 +14,9 @@
 #ifndef OX_KB_MINSEG
 #define OX_KB_MINSEG 32 // smallest contiguous segment (bytes) of the transposed layout a row tile may touch
 #endif
+#ifndef OX_KB_WINPF
+#define OX_KB_WINPF 0    // full row pass: prefetch the window operands one butterfly ahead (experiment)
+#endif
 #ifndef OX_KB_MINB_C2R
 #define OX_KB_MINB_C2R 2 // the same for the c2r-only row pass (no forward transform: fewer live registers)
 #endif
@@ -141,22 +144,37 @@ struct PackLoad {
 // last-stage output of the c2r transform: z[n] = x[2n] + i x[2n+1]; store the map, apply the taper and
 // KEEP the element in registers: the outputs u + m*NT of a thread's last stage are exactly the inputs
 // of its first forward butterfly, so the real-space row never goes back to shared memory
-template <typename T, bool OUT_MAP, bool WIN, bool RUNTIME>
+template <typename T, bool OUT_MAP, bool WIN, bool RUNTIME, int NT>
 struct WindowKeep {
   typedef typename V2<T>::type T2;
   T2 *keep;          // registers [16]
   T2 *map_row;       // global or null
   const T2 *win_row; // global or null
+  int u;             // thread index within the row
+  T2 *w;             // registers [16]: window operands in flight (only a butterfly's worth is live at a time)
   // RUNTIME: test the pointers per element instead of the compile-time flags.  The branches keep the
   // compiler from issuing all 16 window loads at once, which is what the full c2r -> taper -> r2c pass
   // wants (it has no registers to spare: hoisting spilled 40 B/thread and cost 15%); the one-way passes
-  // have free registers and gain 1.5x from the hoisted loads.
+  // have free registers and gain 1.5x from the hoisted loads.  For the full pass the engine prefetches
+  // the window operands one butterfly ahead instead (pre/use).
+  static constexpr bool PREFETCH = OX_KB_WINPF && RUNTIME;
+  __device__ __forceinline__ void pre(int m) const {
+    if (win_row != nullptr) w[m] = ldg2(win_row + u + m * NT);
+  }
+  __device__ __forceinline__ void use(int n, T2 z, int m) const {
+    if (map_row != nullptr) map_row[n] = z;
+    if (win_row != nullptr) {
+      z.x *= w[m].x;
+      z.y *= w[m].y;
+    }
+    keep[m] = z;
+  }
   __device__ __forceinline__ void operator()(int n, T2 z, int m) const {
     if (RUNTIME ? map_row != nullptr : OUT_MAP) map_row[n] = z;
     if (RUNTIME ? win_row != nullptr : WIN) {
-      T2 w = ldg2(win_row + n);
-      z.x *= w.x;
-      z.y *= w.y;
+      T2 w1 = ldg2(win_row + n);
+      z.x *= w1.x;
+      z.y *= w1.y;
     }
     keep[m] = z;
   }
@@ -190,8 +208,11 @@ fused_row_kernel(RowArgs<T> a) {
   const long long rowoff = (long long)(iy0 + f) * MX;
   T2 keep[16];
   constexpr bool RT = IN_H && OUT_H;  // the full pass takes map_out / window as run-time options
-  WindowKeep<T, OUT_MAP, WIN, RT> wst;
+  T2 wpf[16];
+  WindowKeep<T, OUT_MAP, WIN, RT, NT> wst;
   wst.keep = keep;
+  wst.w = wpf;
+  wst.u = u;
   wst.map_row = (RT ? a.map_out != nullptr : OUT_MAP) ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
   const long long grp = plane / a.group, sub = plane - grp * a.group;
   wst.win_row = (RT ? a.window != nullptr : WIN) ? reinterpret_cast<const T2 *>(a.window + grp * a.win_group_stride) + rowoff : nullptr;
