@@ -239,6 +239,11 @@ int ox_split_lensing_combine(const void *khat, int where, int dtype, int nsplits
 int ox_ilc(const void *kmaps, const double *cinv, const double *response_a, const double *response_b, int nfreq, long long npix,
            int where, int mode, void *out, int out_where);
 
+/* enmap.multi_pow(mat, exp, axes=[0,1]) as MapGen uses it for a 2-D covariance (maps.py:1571): per-pixel power of
+ * the symmetric n x n matrices mat[n][n][npix] (float64, n <= 4) through a Jacobi eigen-decomposition; for a
+ * non-integer or negative exponent, eigenvalues that are negative or below 1e-13 of the largest are zeroed. */
+int ox_multi_pow(const double *mat, int n, long long npix, double exponent, int where, double *out, int out_where);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,7 @@ SIGNATURES = {
     "ox_noise_from_splits": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i],
     "ox_split_lensing_combine": [_vp, _i, _i, _i, C.c_longlong, _d, _vp, _i],
     "ox_ilc": [_vp, _vp, _vp, _vp, _i, C.c_longlong, _i, _i, _vp, _i],
+    "ox_multi_pow": [_vp, _i, C.c_longlong, _d, _i, _vp, _i],
 }
 
 for _name, _args in SIGNATURES.items():

@@ -355,3 +355,129 @@ extern "C" int ox_ilc(const void *kmaps, const double *cinv, const double *respo
   OX_CUDA(cudaStreamSynchronize(g_stream));
   return OX_OK;
 }
+
+// ---- enmap.multi_pow (pixell utils.eigpow on axes [0,1]; maps.py:1571): per-pixel symmetric matrix power
+namespace {
+
+constexpr int MP_MAXN = 4;
+
+// cyclic Jacobi on a symmetric n x n matrix held in registers: A -> diag(E), V accumulates the rotations
+template <int N>
+__device__ __forceinline__ void jacobi_eig(double (&A)[N][N], double (&V)[N][N]) {
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; sweep++) {
+    double off = 0.0, dia = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      dia += A[i][i] * A[i][i];
+#pragma unroll
+      for (int j = i + 1; j < N; j++) off += A[i][j] * A[i][j];
+    }
+    if (!(off > 1e-36 * dia)) break;  // off-diagonal norm below 1e-18 of the diagonal (also stops on NaN / zero)
+#pragma unroll
+    for (int p = 0; p < N; p++)
+#pragma unroll
+      for (int q = p + 1; q < N; q++) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+        for (int k = 0; k < N; k++) {  // A <- A J
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {  // A <- J^T A
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+// out = V diag(f(E)) V^T with f = x^e; for non-integer or negative e eigenvalues that are negative or tiny
+// relative to the largest are set to zero first (the eigpow convention the reference relies on for covsqrt)
+template <int N>
+__global__ void multi_pow_kernel(const double *__restrict__ mat, long long n, double e, int clip, double *__restrict__ out) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double A[N][N], V[N][N], E[N];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) A[i][j] = mat[((long long)i * N + j) * n + p];
+  if (N == 1) {
+    const double a = A[0][0];
+    out[p] = clip ? (a > 0.0 ? pow(fabs(a), e) : 0.0) : pow(a, e);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = i + 1; j < N; j++) A[i][j] = A[j][i] = 0.5 * (A[i][j] + A[j][i]);
+  jacobi_eig<N>(A, V);
+  double emax = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i++) emax = fmax(emax, fabs(A[i][i]));
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const double x = A[i][i];
+    if (clip) {
+      const bool bad = (x < emax * 1e-15 * 100.0) || (x < 2.2250738585072014e-308 * 1e4);
+      E[i] = bad ? 0.0 : pow(fabs(x), e);
+    } else {
+      E[i] = pow(x, e);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; k++) acc += V[i][k] * E[k] * V[j][k];
+      out[((long long)i * N + j) * n + p] = acc;
+    }
+}
+
+}  // namespace
+
+extern "C" int ox_multi_pow(const double *mat, int n, long long npix, double exponent, int where, double *out, int out_where) {
+  OX_REQUIRE(mat && out, "ox_multi_pow: null pointer");
+  OX_REQUIRE(n >= 1 && n <= MP_MAXN, "multi_pow supports 1..%d components (got %d)", MP_MAXN, n);
+  OX_REQUIRE(npix >= 1, "multi_pow: empty map");
+  const size_t bytes = sizeof(double) * (size_t)n * n * npix;
+  DevBuf b, o;
+  const void *d;
+  OX_TRY(stage_in(mat, where, bytes, b, &d));
+  double *dst = out;
+  if (out_where == OX_HOST) {
+    OX_TRY(o.ensure(bytes));
+    dst = o.as<double>();
+  }
+  const int clip = (exponent != floor(exponent) || exponent < 0.0) ? 1 : 0;
+  const unsigned g = blocks(npix);
+  switch (n) {
+    case 1: multi_pow_kernel<1><<<g, ST, 0, g_stream>>>((const double *)d, npix, exponent, clip, dst); break;
+    case 2: multi_pow_kernel<2><<<g, ST, 0, g_stream>>>((const double *)d, npix, exponent, clip, dst); break;
+    case 3: multi_pow_kernel<3><<<g, ST, 0, g_stream>>>((const double *)d, npix, exponent, clip, dst); break;
+    default: multi_pow_kernel<4><<<g, ST, 0, g_stream>>>((const double *)d, npix, exponent, clip, dst); break;
+  }
+  OX_KERNEL_CHECK();
+  if (out_where == OX_HOST) OX_TRY(stage_out(out, OX_HOST, dst, bytes));
+  OX_CUDA(cudaStreamSynchronize(g_stream));
+  return OX_OK;
+}

@@ -75,6 +75,19 @@ def _eigpow(A, e):
     return np.moveaxis(np.einsum("...ik,...k,...jk->...ij", V, Ee, V), (-2, -1), (0, 1))
 
 
+def multi_pow(mat, exp):
+    """enmap.multi_pow(mat, exp) on axes [0,1] of a (ncomp, ncomp, Ny, Nx) stack of symmetric matrices
+    (maps.py:1571): per-pixel eigen-decomposition and power on the device (ox_multi_pow)."""
+    A = np.ascontiguousarray(mat, dtype=np.float64)
+    if A.ndim < 3 or A.shape[0] != A.shape[1]:
+        raise ValueError("multi_pow expects (ncomp, ncomp, ...) matrices")
+    if A.shape[0] > 4:
+        raise NotImplementedError("multi_pow on the device supports up to 4 components")
+    out = np.empty_like(A)
+    check(lib.ox_multi_pow(ptr(A), A.shape[0], int(np.prod(A.shape[2:])), C.c_double(float(exp)), OX_HOST, ptr(out), OX_HOST))
+    return out
+
+
 def _sym_convolve(a, b):
     sa = np.concatenate([a, a[:, -2:0:-1]], -1)
     sb = np.concatenate([b, b[:, -2:0:-1]], -1)
@@ -145,7 +158,7 @@ class MapGen(object):
                     cov = cov * np.prod(shape[-2:]) / self.geometry.area
                 if ndown:
                     raise NotImplementedError("ndown (downsample_power) is outside the accelerated path")
-                self.covsqrt = ndmap(_eigpow(cov, 0.5), wcs)
+                self.covsqrt = ndmap(multi_pow(cov, 0.5), wcs)
             else:
                 self.covsqrt = spec2flat(shape, wcs, cov, 0.5, mode="constant", smooth=smooth, method=method)
         cs = np.asarray(self.covsqrt, dtype=np.float64)

@@ -361,3 +361,38 @@ def test_fp32_fused_pipeline_philox_within_1e5(pol, theory):
         p2o = ofc.power2d(mo)[0]
         want = ob.bin(p2o[0, 0] if pol else p2o)[1]
         assert np.max(np.abs(bp[i, 0] - want) / np.max(np.abs(want))) < TOL32
+
+
+def test_multi_pow_on_device_matches_eigpow(theory):
+    """enmap.multi_pow for a 2-D covariance (maps.py:1571) as a per-pixel Jacobi eigen-power on the device vs the
+    oracle's numpy eigh: random SPD matrices, exactly singular ones (B = 0, |TE|^2 = TT EE), zero and negative
+    eigenvalues (clipped for the square root), n = 1..3, integer and fractional exponents; then MapGen built from
+    a 4-D covariance reproduces the map of the 3-D one."""
+    from orphics_b200 import maps
+    rng = np.random.RandomState(17)
+    npix = 4000
+    for n in (1, 2, 3):
+        A = rng.standard_normal((npix, n, n))
+        S = A @ A.transpose(0, 2, 1)
+        # (ridge: condition numbers <~ 100, so that LAPACK's absolute eigenvalue accuracy does not limit the
+        # comparison of the inverse powers at 1e-10)
+        S = (S + 0.3 * np.eye(n) * np.trace(S, axis1=1, axis2=2)[:, None, None] / n) * rng.uniform(1e-3, 1e3, (npix, 1, 1))
+        S[:50] = 0.0                                     # zero matrices
+        if n > 1:
+            S[50:100, -1, :] = 0.0; S[50:100, :, -1] = 0.0           # exactly singular (one vanishing component)
+            v = rng.standard_normal((50, n, 1)); S[100:150] = v @ v.transpose(0, 2, 1)   # rank one
+            S[150:200] -= 0.6 * np.eye(n) * np.trace(S[150:200], axis1=1, axis2=2)[:, None, None] / n   # indefinite
+        mat = np.ascontiguousarray(S.transpose(1, 2, 0)).reshape(n, n, 40, 100)
+        for e in (0.5, -0.5, -1.0, 2.0, 1.0):
+            got = maps.multi_pow(mat, e)
+            want = oenmap.eigpow(mat, e)
+            scale = np.max(np.abs(want.reshape(n * n, -1)), axis=0).reshape(40, 100) + 1e-300
+            assert np.max(np.abs(got - want) / scale) < 1e-10, (n, e)
+    # MapGen from a 2-D (4-D array) covariance: same covsqrt, same map as from the 1-D spectra
+    shape, wcs, so, wo, modl, ps = setup(128, 2.0, True, theory)
+    og = omaps.MapGen(so, wo, ps)
+    cs3 = np.asarray(og.covsqrt)
+    cov4 = np.einsum("abyx,cbyx->acyx", cs3, cs3)         # covsqrt^2 per pixel, already in pixel units
+    mg = maps.MapGen(shape, wcs, cov4, pixel_units=True)
+    assert relerr(mg.covsqrt, cs3) < 1e-9
+    assert relerr(mg.get_map(seed=3), og.get_map(seed=3)) < 1e-9
