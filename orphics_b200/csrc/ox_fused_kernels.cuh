@@ -41,10 +41,27 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
 __device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
 
+#ifndef OX_STREAM_ST
+#define OX_STREAM_ST 0   // 1: planes written once and read by the next kernel are stored with the streaming hint
+#endif
+#ifndef OX_STREAM_LD
+#define OX_STREAM_LD 0   // 1: planes read once are loaded with the streaming hint (no L1 allocation)
+#endif
+__device__ __forceinline__ void st_once(double2 *p, double2 v) {
+  if (OX_STREAM_ST) __stcs(p, v);
+  else *p = v;
+}
+__device__ __forceinline__ void st_once(float2 *p, float2 v) {
+  if (OX_STREAM_ST) __stcs(p, v);
+  else *p = v;
+}
+__device__ __forceinline__ double2 ld_once(const double2 *p) { return OX_STREAM_LD ? __ldcs(p) : *p; }
+__device__ __forceinline__ float2 ld_once(const float2 *p) { return OX_STREAM_LD ? __ldcs(p) : *p; }
+
 template <typename T2>
 struct GlobalStore {
   T2 *dst;
-  __device__ __forceinline__ void operator()(int f, T2 v, int) const { dst[f] = v; }
+  __device__ __forceinline__ void operator()(int f, T2 v, int) const { st_once(dst + f, v); }
 };
 
 // first-stage input held in registers (m is a compile-time constant after unrolling)
@@ -57,7 +74,7 @@ struct RegLoad {
 template <typename T2>
 struct GlobalLoad {
   const T2 *src;
-  __device__ __forceinline__ T2 operator()(int e, int) const { return src[e]; }
+  __device__ __forceinline__ T2 operator()(int e, int) const { return ld_once(src + e); }
 };
 
 // max_carveout: ask for the largest shared-memory carve-out so that occupancy is set by the registers.  Only
@@ -162,7 +179,7 @@ struct WindowKeep {
     if (win_row != nullptr) w[m] = ldg2(win_row + u + m * NT);
   }
   __device__ __forceinline__ void use(int n, T2 z, int m) const {
-    if (map_row != nullptr) map_row[n] = z;
+    if (map_row != nullptr) st_once(map_row + n, z);
     if (win_row != nullptr) {
       z.x *= w[m].x;
       z.y *= w[m].y;
@@ -170,7 +187,7 @@ struct WindowKeep {
     keep[m] = z;
   }
   __device__ __forceinline__ void operator()(int n, T2 z, int m) const {
-    if (RUNTIME ? map_row != nullptr : OUT_MAP) map_row[n] = z;
+    if (RUNTIME ? map_row != nullptr : OUT_MAP) st_once(map_row + n, z);
     if (RUNTIME ? win_row != nullptr : WIN) {
       T2 w1 = ldg2(win_row + n);
       z.x *= w1.x;
@@ -294,8 +311,8 @@ fused_row_kernel(RowArgs<T> a) {
     x0.y = (T)0.5 * (sum.y - pw.y);
     x1.x = (T)0.5 * (sum.x + pw.x);
     x1.y = -(T)0.5 * (sum.y + pw.y);
-    dst[(long long)k * a.ny + r] = x0;
-    if (2 * k != MX) dst[(long long)(MX - k) * a.ny + r] = x1;
+    st_once(dst + (long long)k * a.ny + r, x0);
+    if (2 * k != MX) st_once(dst + (long long)(MX - k) * a.ny + r, x1);
   }
 }
 
