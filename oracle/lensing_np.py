@@ -2,7 +2,9 @@
 /root/reference/orphics/lensing.py: fkappa_to_fphi / kappa_to_phi (:651-665), flat_taylens
 (:395-440) and FlatLensingSims.get_sim (:499-521) with flat_taylens in place of
 pixell.lensing.displace_map (third-party spline remap, out of the path's scope).
-PARITY UNPINNED for the pixell pieces (enmap.fft(normalize='phys'), laxes, pixshape)."""
+The function bodies are pinned by tests/golden/lensing_refbody.npz (the reference's own flat_taylens / kappa_to_phi
+run unmodified over oracle/enmap_np.py); PARITY UNPINNED for the pixell pieces underneath (enmap.fft(normalize='phys'),
+laxes, pixshape)."""
 from math import comb, factorial
 
 import numpy as np

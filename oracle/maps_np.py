@@ -1,7 +1,8 @@
 """ORACLE (test infrastructure) -- numpy restatement of the orphics.maps hot path.
 
-PARITY UNPINNED for everything that goes through pixell (see oracle/__init__.py).
-Each function cites the /root/reference/orphics/maps.py lines it follows.
+The logic orphics owns is pinned by goldens made from the reference's own bodies (tests/golden/maps_refbody.npz,
+split_callers.npz, ilc.npz); PARITY UNPINNED for what goes through pixell underneath (oracle/enmap_np.py, see
+oracle/__init__.py).  Each function cites the /root/reference/orphics/maps.py lines it follows.
 """
 import numpy as np
 

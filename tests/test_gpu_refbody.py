@@ -56,3 +56,17 @@ def test_helpers_match_reference_bodies():
     assert np.array_equal(np.asarray(maps.mask_kspace(shape, wcs, lmin=300, lmax=2000)), G["T_mask_l"])
     assert np.array_equal(np.asarray(maps.mask_kspace(shape, wcs, lxcut=90, lycut=50, lmax=4000)), G["T_mask_xy"])
     assert relerr(maps.filter_map(maps.ndmap(G["T_map11"], wcs), G["T_beam"] * G["T_mask_l"]), G["T_filtered"]) < TOL
+
+
+def test_lensing_callers_match_reference_bodies():
+    """lensing.flat_taylens / kappa_to_phi / fkappa_to_fphi on device FFTs vs the reference's own bodies."""
+    from orphics_b200 import maps, lensing
+    GL = np.load(os.path.join(ROOT, "tests", "golden", "lensing_refbody.npz"))
+    shape, wcs = maps.rect_geometry(width_arcmin=64 * 2.0, px_res_arcmin=2.0, height_arcmin=48 * 2.0)
+    assert tuple(shape) == (48, 64)
+    modl = maps.Geometry.get(shape, wcs).modlmap()
+    assert relerr(lensing.kappa_to_phi(maps.ndmap(GL["kappa"], wcs), modl), GL["phi"]) < TOL
+    assert relerr(lensing.fkappa_to_fphi(np.fft.fft2(GL["kappa"]), modl), GL["fk2fp"]) < 1e-13
+    for order in (2, 5):
+        got = lensing.flat_taylens(maps.ndmap(GL["phis"], wcs), maps.ndmap(GL["imap"], wcs), order)
+        assert relerr(got, GL[f"lensed_o{order}"]) < TOL

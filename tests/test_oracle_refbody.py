@@ -58,3 +58,19 @@ def test_helpers_restatement():
     assert np.array_equal(np.asarray(omaps.mask_kspace(shape, wcs, lmin=300, lmax=2000)), G["T_mask_l"])
     assert np.array_equal(np.asarray(omaps.mask_kspace(shape, wcs, lxcut=90, lycut=50, lmax=4000)), G["T_mask_xy"])
     assert relerr(omaps.filter_map(oenmap.ndmap(G["T_map11"], wcs), G["T_beam"] * G["T_mask_l"]), G["T_filtered"]) < TOL
+
+
+GL = np.load(os.path.join(ROOT, "tests", "golden", "lensing_refbody.npz"))
+
+
+def test_lensing_callers_restatement():
+    """oracle/lensing_np.py vs the reference's own flat_taylens / kappa_to_phi / fkappa_to_fphi bodies."""
+    from oracle import lensing_np
+    shape, wcs = omaps.rect_geometry(width_arcmin=64 * 2.0, px_res_arcmin=2.0, height_arcmin=48 * 2.0)
+    modl = np.asarray(oenmap.modlmap(shape, wcs))
+    assert relerr(lensing_np.kappa_to_phi(oenmap.ndmap(GL["kappa"], wcs), modl), GL["phi"]) < TOL
+    assert relerr(lensing_np.fkappa_to_fphi(np.fft.fft2(GL["kappa"]), modl), GL["fk2fp"]) < TOL
+    for order in (2, 5):
+        got = lensing_np.flat_taylens(oenmap.ndmap(GL["phis"], wcs), oenmap.ndmap(GL["imap"], wcs), order)
+        assert relerr(got, GL[f"lensed_o{order}"]) < 1e-12
+    assert float(GL["max_shift_pixels"]) > 3      # the integer part of the Taylens displacement is exercised
