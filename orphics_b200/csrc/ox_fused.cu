@@ -39,6 +39,9 @@ using namespace oxk;
 #ifndef OX_KA3_SEQ
 #define OX_KA3_SEQ 0    // three-component K_A: 1 = one CTA of LY/16 threads transforms the components one after the other
 #endif
+#ifndef OX_KA3_UNROLL
+#define OX_KA3_UNROLL 2  // unroll factor of the pixel loop of the three-component K_A
+#endif
 #ifndef OX_KA3_MINB
 #define OX_KA3_MINB 2   // resident CTAs per SM asked of the three-component K_A (384 threads): 2 -> 80 registers, the
                         // 136 B of spills cost less than a lone CTA whose noise and FFT phases cannot overlap
@@ -322,8 +325,9 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
       FFT::template run<+1, true, false>(s + c * PS, tw2, tid, 0, ld, stc);
     }
   } else {
+    constexpr int UR3 = OX_KA3_UNROLL;
     if (ix != 0 && ix != a.mx && a.cov_symmetric && MODE == OX_NOISE_PHILOX_HERMITIAN) {
-#pragma unroll 2
+#pragma unroll UR3
       for (int iy = tid; iy < LY; iy += NTHREADS) {
         T2 z[NC];
         sim_pixel<T, NC, MODE, 2>(a, keys, logtab, noise_sim, ix, mxp, iy, h, z);
@@ -331,7 +335,7 @@ fused_sim_col_kernel(SimColArgs<T> a, typename V2<T>::type *__restrict__ Ht /*[n
         for (int c = 0; c < NC; c++) s[c * PS + pad(iy)] = z[c];
       }
     } else {
-#pragma unroll 2
+#pragma unroll UR3
       for (int iy = tid; iy < LY; iy += NTHREADS) {
         T2 z[NC];
         sim_pixel<T, NC, MODE, 0>(a, keys, logtab, noise_sim, ix, mxp, iy, h, z);
