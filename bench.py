@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--pol", action="store_true", help="IQU sims, 6 spectra (configs[2])")
     ap.add_argument("--no-window", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=6, help="maps timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=24, help="maps timed for cpu_baseline: ~10 s on one host core (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
