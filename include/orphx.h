@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OX_ABI_VERSION 1
+#define OX_ABI_VERSION 2
 
 enum { OX_OK = 0, OX_ERR_INVALID = -1, OX_ERR_CUDA = -2, OX_ERR_CUFFT = -3, OX_ERR_NOMEM = -4, OX_ERR_UNSUPPORTED = -5 };
 enum { OX_F64 = 0, OX_F32 = 1 };
@@ -62,6 +62,7 @@ typedef struct ox_simplan ox_simplan;
 typedef struct ox_powerplan ox_powerplan;
 typedef struct ox_pipeline ox_pipeline;
 typedef struct ox_qeplan ox_qeplan;
+typedef struct ox_comm ox_comm;
 
 /* ---- runtime ------------------------------------------------------------- */
 int ox_abi_version(void);
@@ -93,6 +94,12 @@ int ox_timer_destroy(void *t);
 int ox_launch_count(long long *n);
 /* write `bytes` of zeros to a scratch buffer larger than L2 (bench hygiene) */
 int ox_flush_l2(void);
+/* per-stage device times of whatever runs between begin and end: the library records a CUDA event on its
+ * stream after each named stage (kernel or group of kernels); stage i spent `ms` since the previous mark.
+ * Measurement only (bench.py's roofline.achieved); no reference counterpart. */
+int ox_profile_begin(void);
+int ox_profile_end(int *nstages);
+int ox_profile_stage(int i, char *name, size_t len, float *ms);
 
 /* ---- geometry: enmap.laxes / lmap / modlmap / area (maps.py:1374,1605,1607,1938-1939)
  * ly[ny], lx[nx] are the caller's 2*pi*fftfreq axes (host); area in steradians.   */
@@ -173,8 +180,9 @@ int ox_pipeline_maps(ox_pipeline *pl, void **maps_dev);
 /* one ox_pipeline_run with CUDA events between the stages; stage_ms[6] = sim_fill, cuFFT
  * inverse, window, cuFFT forward, power_bin (+finalize), statistics.  Philox modes only. */
 int ox_pipeline_profile(ox_pipeline *pl, const long long *seeds, int nsim, int noise_mode, int flags, float *stage_ms);
-/* device pointers of the accumulators (for a torch.distributed / NCCL all-reduce in place) */
-int ox_pipeline_stats(ox_pipeline *pl, long long **n_dev, double **sum_dev, double **cross_dev, int *dim);
+/* device pointer of the accumulators, packed so that the reduction over ranks is ONE collective
+ * (stats.py:1215-1217): float64 [N | SUM[dim] | CROSS[dim][dim]], N an exactly represented integer */
+int ox_pipeline_stats(ox_pipeline *pl, double **packed_dev, int *dim);
 int ox_pipeline_stats_reset(ox_pipeline *pl);
 
 /* ---- lensing.qest (tutorials/tt_verification.ipynb:81,608,610; lensing.py:973-976) */
@@ -193,9 +201,9 @@ int ox_qeplan_destroy(ox_qeplan *q);
  * accumulate_meanfield: add every kappa_hat(l) (half plane) and nbatch to the plan's mean-field stack. */
 int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int nbatch, int already_ft, int return_ft,
                       int accumulate_meanfield, void *kappa_out, int out_where);
-/* device pointers of the mean-field stack (complex128 [ny][nx/2+1] sum of kappa_hat(l)) and its int64
- * count, for an in-place NCCL all-reduce (Statistics.add_stack / allreduce, stats.py:1134-1158,1227-1228) */
-int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem);
+/* device pointer of the mean-field accumulator, packed for ONE collective (Statistics.add_stack / allreduce,
+ * stats.py:1134-1158,1227-1228): float64 [2*nelem: complex128 [ny][nx/2+1] sum of kappa_hat(l) | count | pad] */
+int ox_qe_meanfield(ox_qeplan *q, double **packed_dev, long long *nelem);
 int ox_qe_meanfield_reset(ox_qeplan *q);
 /* which implementation the plan runs for Hermitian inputs: 0 = full-plane c2c chain on cuFFT (unsymmetric
  * filters, or EB on maps that are not powers of two), 1 = TT on half planes with cuFFT r2c/c2r, 2 = TT and
@@ -243,6 +251,23 @@ int ox_ilc(const void *kmaps, const double *cinv, const double *response_a, cons
  * the symmetric n x n matrices mat[n][n][npix] (float64, n <= 4) through a Jacobi eigen-decomposition; for a
  * non-integer or negative exponent, eigenvalues that are negative or below 1e-13 of the largest are zeroed. */
 int ox_multi_pow(const double *mat, int n, long long npix, double exponent, int where, double *out, int out_where);
+
+/* ---- the exchange step: Statistics.allreduce (stats.py:1184-1232, mpi4py Allreduce(SUM)) as NCCL sum
+ * all-reduces over NVLink, one process per GPU.  Rank 0 obtains the 128-byte NCCL unique id and the host
+ * hands it to the other ranks (torch.distributed store, MPI_Bcast, a file); every rank then creates its
+ * communicator on its current device.  nranks == 1 needs no id and makes every reduction a no-op.
+ * NCCL is bound at run time (dlopen libnccl.so.2, or $ORPHX_NCCL_LIB). */
+#define OX_COMM_ID_BYTES 128
+int ox_comm_unique_id(void *id, size_t len);
+int ox_comm_create(int rank, int nranks, const void *id, size_t len, ox_comm **out);
+int ox_comm_destroy(ox_comm *c);
+int ox_comm_info(ox_comm *c, int *rank, int *nranks, int *nccl_version);
+/* in-place sum over the ranks of count float64 values in device memory, on the library stream */
+int ox_comm_allreduce_f64(ox_comm *c, double *buf_dev, long long count);
+/* ONE ncclAllReduce of the pipeline's packed [N | SUM | CROSS] (stats.py:1215-1217) */
+int ox_pipeline_allreduce(ox_comm *c, ox_pipeline *pl);
+/* ONE ncclAllReduce of the estimator's packed [mean-field stack | count] (stats.py:1227-1228) */
+int ox_qe_meanfield_allreduce(ox_comm *c, ox_qeplan *q);
 
 #ifdef __cplusplus
 }

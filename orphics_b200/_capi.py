@@ -68,6 +68,9 @@ SIGNATURES = {
     "ox_timer_destroy": [_vp],
     "ox_launch_count": [_pll],
     "ox_flush_l2": [],
+    "ox_profile_begin": [],
+    "ox_profile_end": [C.POINTER(_i)],
+    "ox_profile_stage": [_i, C.c_char_p, _sz, C.POINTER(C.c_float)],
     "ox_geometry_create": [_i, _i, _vp, _vp, _d, _pvp],
     "ox_geometry_destroy": [_vp],
     "ox_geometry_modlmap": [_vp, _vp, _i],
@@ -96,12 +99,19 @@ SIGNATURES = {
     "ox_pipeline_path": [_vp, C.POINTER(_i)],
     "ox_pipeline_maps": [_vp, _pvp],
     "ox_pipeline_profile": [_vp, _vp, _i, _i, _i, C.POINTER(C.c_float)],
-    "ox_pipeline_stats": [_vp, _pvp, _pvp, _pvp, C.POINTER(_i)],
+    "ox_pipeline_stats": [_vp, _pvp, C.POINTER(_i)],
     "ox_pipeline_stats_reset": [_vp],
     "ox_qeplan_create": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _pvp],
     "ox_qeplan_destroy": [_vp],
     "ox_qe_reconstruct": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i],
-    "ox_qe_meanfield": [_vp, _pvp, _pvp, _pll],
+    "ox_qe_meanfield": [_vp, _pvp, _pll],
+    "ox_comm_unique_id": [_vp, _sz],
+    "ox_comm_create": [_i, _i, _vp, _sz, _pvp],
+    "ox_comm_destroy": [_vp],
+    "ox_comm_info": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
+    "ox_comm_allreduce_f64": [_vp, _vp, _ll],
+    "ox_pipeline_allreduce": [_vp, _vp],
+    "ox_qe_meanfield_allreduce": [_vp, _vp],
     "ox_qe_meanfield_reset": [_vp],
     "ox_qe_path": [_vp],
     "ox_fft_c2c": [_vp, _vp, _i, _i, _i, _d, _vp, _i],
@@ -257,6 +267,32 @@ class Timer:
             lib.ox_timer_destroy(self._t)
         except Exception:
             pass
+
+
+class StageProfile:
+    """with StageProfile() as p: ...calls...; p.stages -> [(name, ms)] from CUDA events between the library's
+    stage marks (ox_profile_*)."""
+
+    def __enter__(self):
+        check(lib.ox_profile_begin())
+        self.stages = []
+        return self
+
+    def __exit__(self, *exc):
+        n = C.c_int(0)
+        check(lib.ox_profile_end(C.byref(n)))
+        buf = C.create_string_buffer(64)
+        for i in range(n.value):
+            ms = C.c_float(0)
+            check(lib.ox_profile_stage(i, buf, 64, C.byref(ms)))
+            self.stages.append((buf.value.decode(), float(ms.value)))
+        return False
+
+    def totals(self):
+        out = {}
+        for name, ms in self.stages:
+            out[name] = out.get(name, 0.0) + ms
+        return out
 
 
 def launch_count():

@@ -84,7 +84,7 @@ __global__ void half_index_kernel(const uint16_t *__restrict__ idx, int ny, int 
   }
 }
 
-__global__ void invcount_kernel(const unsigned long long *__restrict__ counts, int nslots, double *__restrict__ inv) {
+__global__ void countf64_kernel(const unsigned long long *__restrict__ counts, int nslots, double *__restrict__ inv) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < nslots) inv[s] = (double)counts[s];
 }
@@ -194,6 +194,7 @@ power_bin_half_kernel(const T2 *__restrict__ k1, const T2 *__restrict__ k2, cons
   for (int s = lane; s < NS * stride; s += 32) mine[s] = 0.0;
   __syncwarp();
   const long long m = blockIdx.y;
+  const int ny = (int)(nh / nxh);
   const T2 *a = k1 + m * NC * nh;
   const T2 *b = CROSS ? k2 + m * NC * nh : a;
   long long begin = (long long)blockIdx.x * BIN_CHUNK;
@@ -226,38 +227,49 @@ power_bin_half_kernel(const T2 *__restrict__ k1, const T2 *__restrict__ k2, cons
           bi[c] = (double)y.y;
         }
       }
+      double c = 1.0, s = 0.0;
+      bool nyq_pair = false;
       if (ROT && NC == 3) {
         int iy = (int)(i / nxh), ix = (int)(i - (long long)iy * nxh);
         double y = ly[iy], x = lx[ix];
         double l2 = y * y + x * x;
-        double c = 1.0, s = 0.0;
         if (l2 > 0.0) {
           double inv = 1.0 / l2;
           c = (y * y - x * x) * inv;            // cos 2*atan2(-lx,ly)
           s = rot_sgn * (-2.0 * x * y) * inv;   // sgn * sin 2*atan2(-lx,ly)
         }
-        double er = c * ar[1] - s * ar[2], ei = c * ai[1] - s * ai[2];
-        double fr = s * ar[1] + c * ar[2], fi = s * ai[1] + c * ai[2];
-        ar[1] = er; ai[1] = ei; ar[2] = fr; ai[2] = fi;
-        if (CROSS) {
-          er = c * br[1] - s * br[2]; ei = c * bi[1] - s * bi[2];
-          fr = s * br[1] + c * br[2]; fi = s * bi[1] + c * bi[2];
-          br[1] = er; bi[1] = ei; br[2] = fr; bi[2] = fi;
-        }
+        // Nyquist row of an interior column: the mirrored pixel p' = (iy, nx - ix) has the same ly and the
+        // opposite lx, so its rotation has the opposite sine and its E/B power differs from the one at p:
+        // the pair is accumulated as one term with +s and one with -s instead of twice the term at p
+        nyq_pair = (2 * iy == ny) && w == 2.0;
       }
       if (!CROSS) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) { br[c] = ar[c]; bi[c] = ai[c]; }
+        for (int c2 = 0; c2 < NC; c2++) { br[c2] = ar[c2]; bi[c2] = ai[c2]; }
       }
-      if (SKIP_CROSS) {
+      const int nterm = nyq_pair ? 2 : 1;
+      const double wt = nyq_pair ? 1.0 : w;
+      for (int term = 0; term < nterm; term++) {
+        double pr[NC], pi[NC], qr[NC], qi[NC];
 #pragma unroll
-        for (int c = 0; c < NC; c++) v[c] = (ar[c] * br[c] + ai[c] * bi[c]) * w;
-      } else {
-        int s = 0;
+        for (int c2 = 0; c2 < NC; c2++) { pr[c2] = ar[c2]; pi[c2] = ai[c2]; qr[c2] = br[c2]; qi[c2] = bi[c2]; }
+        if (ROT && NC == 3) {
+          const double st = term ? -s : s;
+          pr[1] = c * ar[1] - st * ar[2]; pi[1] = c * ai[1] - st * ai[2];
+          pr[2] = st * ar[1] + c * ar[2]; pi[2] = st * ai[1] + c * ai[2];
+          qr[1] = c * br[1] - st * br[2]; qi[1] = c * bi[1] - st * bi[2];
+          qr[2] = st * br[1] + c * br[2]; qi[2] = st * bi[1] + c * bi[2];
+        }
+        if (SKIP_CROSS) {
 #pragma unroll
-        for (int p = 0; p < NC; p++)
+          for (int c2 = 0; c2 < NC; c2++) v[c2] += (pr[c2] * qr[c2] + pi[c2] * qi[c2]) * wt;
+        } else {
+          int sidx = 0;
 #pragma unroll
-          for (int q = p; q < NC; q++) v[s++] = (ar[p] * br[q] + ai[p] * bi[q]) * w;
+          for (int p = 0; p < NC; p++)
+#pragma unroll
+            for (int q = p; q < NC; q++) v[sidx++] += (pr[p] * qr[q] + pi[p] * qi[q]) * wt;
+        }
       }
     }
     unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -304,9 +316,9 @@ int finish_binner(ox_binner *b) {
   int nslots = b->nslots;
   b->h_counts.resize(nslots);
   OX_CUDA(cudaMemcpyAsync(b->h_counts.data(), b->counts.p, sizeof(long long) * nslots, cudaMemcpyDeviceToHost, g_stream));
-  OX_TRY(b->invcount.ensure(sizeof(double) * nslots));
-  invcount_kernel<<<(nslots + 127) / 128, 128, 0, g_stream>>>(b->counts.as<unsigned long long>(), nslots,
-                                                             b->invcount.as<double>());
+  OX_TRY(b->countf.ensure(sizeof(double) * nslots));
+  countf64_kernel<<<(nslots + 127) / 128, 128, 0, g_stream>>>(b->counts.as<unsigned long long>(), nslots,
+                                                             b->countf.as<double>());
   OX_KERNEL_CHECK();
   OX_CUDA(cudaStreamSynchronize(g_stream));
   return OX_OK;
@@ -413,7 +425,7 @@ int power_bin_half(ox_geometry *g, ox_binner *b, int dtype, int ncomp, const voi
   dim3 grid((ns * nbins + 127) / 128, nbatch);
   double nf = (flags & OX_FLAG_PIXEL_UNITS) ? 1.0 : normfact;
   bandpower_finalize_kernel<<<grid, 128, 0, g_stream>>>(partial.as<double>(), nblk, ns, b->nslots,
-                                                        b->invcount.as<double>(), nf, bp_dev);
+                                                        b->countf.as<double>(), nf, bp_dev);
   OX_KERNEL_CHECK();
   return OX_OK;
 }

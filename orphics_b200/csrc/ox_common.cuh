@@ -108,6 +108,8 @@ static inline size_t elem_size(int dtype) { return dtype == OX_F32 ? 4 : 8; }
 
 // number of SMs of the current device (cached)
 int sm_count();
+// records a CUDA event named after the stage that just finished (no-op unless ox_profile_begin is active)
+void stage_mark(const char *name);
 
 }  // namespace ox
 
@@ -130,7 +132,7 @@ struct ox_binner {
   bool has_half = false;
   int ny = 0, nx = 0, nxh = 0;
   ox::DevBuf idxh;      // uint16[ny*nxh]: slot | (weight==2 ? 0x8000 : 0)
-  ox::DevBuf invcount;  // double[nslots]: 1/count
+  ox::DevBuf countf;  // double[nslots]: the integer slot counts as float64 (divisor of the bandpower sums)
   ox::DevBuf scratch, partial, stage;
 };
 
@@ -187,9 +189,12 @@ struct ox_pipeline {
   ox_binner *b = nullptr;
   ox::DevBuf window;  // T[ny][nx] or empty
   bool has_window = false;
+  bool maps_valid = false;  // the last run left its real-space maps in s->maps
   int nspec = 1, nbins = 0, dim = 0;
   ox::DevBuf partial, bp;            // partial sums, bandpowers [max_batch][nspec][nbins]
-  ox::DevBuf stat_n, stat_sum, stat_cross;
+  // Statistics triple packed for ONE all-reduce (stats.py:1215-1217): float64 [N | SUM[dim] | CROSS[dim][dim]],
+  // N kept as an exactly representable integer
+  ox::DevBuf stat;
 };
 
 // ---- cross-file internal entry points -------------------------------------------
@@ -214,6 +219,8 @@ int power_bin_half(ox_geometry *g, ox_binner *b, int dtype, int ncomp, const voi
                    int flags, double normfact, DevBuf &partial, double *bp_dev);
 // dst[n] (dtype) = src[n] (float64), both on the device
 int cast_from_f64(const double *src_dev, void *dst_dev, long long n, int dtype);
+// in-place NCCL sum of count float64 values on the library stream (ox_comm.cu)
+int comm_allreduce_f64(ox_comm *c, double *buf_dev, long long count);
 // maps[n] *= window[npix] (in place, broadcast over planes)
 int apply_window(int dtype, void *maps, const void *window, long long npix, long long nplanes);
 }  // namespace ox

@@ -38,6 +38,20 @@ int stage_out(void *dst, int where, const void *dev_src, size_t bytes) {
   return OX_OK;
 }
 
+// ---- stage profiler: CUDA events between named marks on the library stream (bench.py's per-kernel times)
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_ev;
+static std::vector<std::string> g_prof_names;
+
+void stage_mark(const char *name) {
+  if (!g_prof_on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, g_stream);
+  g_prof_ev.push_back(e);
+  g_prof_names.push_back(name);
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -53,6 +67,32 @@ int sm_count() {
 }  // namespace ox
 
 using namespace ox;
+
+extern "C" {
+int ox_profile_begin(void) {
+  for (auto e : g_prof_ev) cudaEventDestroy(e);
+  g_prof_ev.clear();
+  g_prof_names.clear();
+  g_prof_on = true;
+  stage_mark("begin");
+  return OX_OK;
+}
+
+int ox_profile_end(int *nstages) {
+  OX_REQUIRE(nstages, "null pointer");
+  g_prof_on = false;
+  if (!g_prof_ev.empty()) OX_CUDA(cudaEventSynchronize(g_prof_ev.back()));
+  *nstages = g_prof_ev.empty() ? 0 : (int)g_prof_ev.size() - 1;
+  return OX_OK;
+}
+
+int ox_profile_stage(int i, char *name, size_t len, float *ms) {
+  OX_REQUIRE(name && ms && i >= 0 && i + 1 < (int)g_prof_ev.size(), "ox_profile_stage: stage %d out of range", i);
+  snprintf(name, len, "%s", g_prof_names[i + 1].c_str());
+  OX_CUDA(cudaEventElapsedTime(ms, g_prof_ev[i], g_prof_ev[i + 1]));
+  return OX_OK;
+}
+}
 
 // ---- cuFFT plan cache ------------------------------------------------------------
 FFTPlans::~FFTPlans() {

@@ -443,18 +443,31 @@ fused_col_bin_kernel(ColBinArgs<T> a, double *__restrict__ partial /*[nbatch][gr
             re[c] = (double)z.x;
             im[c] = (double)z.y;
           }
+          double c = 1.0, sn = 0.0;
+          // Nyquist row of an interior column: the mirrored pixel has the opposite lx, hence the opposite
+          // sine of the rotation angle -- its E/B power is accumulated with -sn instead of doubling p's
+          bool nyq_pair = false;
           if (NC == 3 && a.rot) {
-            double c, sn;
             rot_cs(a.ly[iy], x, a.rot_sgn, c, sn);
-            double er = c * re[1] - sn * re[2], ei = c * im[1] - sn * im[2];
-            double br = sn * re[1] + c * re[2], bi = sn * im[1] + c * im[2];
-            re[1] = er; im[1] = ei; re[2] = br; im[2] = bi;
+            nyq_pair = (2 * iy == LY) && (raw & 0x8000u);
           }
-          int q = 0;
+          const int nterm = nyq_pair ? 2 : 1;
+          const double wt = nyq_pair ? 1.0 : w;
+          for (int term = 0; term < nterm; term++) {
+            double pr[NC], pi[NC];
 #pragma unroll
-          for (int i2 = 0; i2 < NC; i2++)
+            for (int c2 = 0; c2 < NC; c2++) { pr[c2] = re[c2]; pi[c2] = im[c2]; }
+            if (NC == 3 && a.rot) {
+              const double st = term ? -sn : sn;
+              pr[1] = c * re[1] - st * re[2]; pi[1] = c * im[1] - st * im[2];
+              pr[2] = st * re[1] + c * re[2]; pi[2] = st * im[1] + c * im[2];
+            }
+            int q = 0;
 #pragma unroll
-            for (int j = i2; j < NC; j++) v[q++] = (re[i2] * re[j] + im[i2] * im[j]) * w;
+            for (int i2 = 0; i2 < NC; i2++)
+#pragma unroll
+              for (int j = i2; j < NC; j++) v[q++] += (pr[i2] * pr[j] + pi[i2] * pi[j]) * wt;
+          }
         }
         unsigned peers = __match_any_sync(0xffffffffu, key);
         bool leader = (__ffs(peers) - 1) == lane;
@@ -681,6 +694,7 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
 #undef OX_SIMCOL
   OX_TRY(st);
   OX_MARK(1);
+  stage_mark("K_A sim+col_ifft");
   RowArgs<T> ra;
   ra.Hin = fs.Ha.as<T2>();
   ra.map_in = nullptr;
@@ -699,6 +713,7 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
   st = launch_row_any<T>(ra, (long long)nsim * nc, PipelineRowModes());
   OX_TRY(st);
   OX_MARK(2);
+  stage_mark("K_B row_c2r+taper+r2c");
   OX_MARK(3);
   OX_MARK(4);
   ColBinArgs<T> ca;
@@ -731,9 +746,10 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
   int nbins = pl->b->nslots - 2;
   dim3 grid((ns * nbins * 32 + 255) / 256, nsim);
   bandpower_finalize2_kernel<<<grid, 256, 0, g_stream>>>(pl->partial.as<double>(), nblk, ns, pl->b->nslots,
-                                                         pl->b->invcount.as<double>(), pl->p->normfact, pl->bp.as<double>());
+                                                         pl->b->countf.as<double>(), pl->p->normfact, pl->bp.as<double>());
   OX_KERNEL_CHECK();
   OX_MARK(5);
+  stage_mark("K_C col_fft+power+bin");
 #undef OX_MARK
   return OX_OK;
 }

@@ -130,6 +130,11 @@ struct RowArgs {
   // input = map_in * window + map_in2 * window2, with map_in2 / window2 addressed like map_in / window
   long long map_in_sub_stride = 0;
   const T *map_in2 = nullptr, *window2 = nullptr;
+  // CTA -> (row tile, plane): planes vary fastest (nplanes_fast = number of planes) so that the CTAs resident
+  // together work on the SAME rows of different planes and a row of a batch-shared window is fetched from DRAM
+  // once per launch instead of once per plane (ncu round 1: 66 MB read per 33.5 MB map with rows fastest);
+  // 0 = rows fastest, blockIdx.y = plane (ORPHX_KB_ORDER=rows)
+  int nplanes_fast = 0;
 };
 
 // first-stage input of the c2r transform: Z[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/Nx} (X[k] - conj X[M-k])
@@ -213,8 +218,13 @@ fused_row_kernel(RowArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T2 *s = reinterpret_cast<T2 *>(smem_raw);  // [R][PS]
   const int tid = threadIdx.x;
-  const int iy0 = blockIdx.x * R;
-  const long long plane = blockIdx.y;
+  int tile = blockIdx.x;
+  long long plane = blockIdx.y;
+  if (a.nplanes_fast) {
+    tile = blockIdx.x / a.nplanes_fast;
+    plane = blockIdx.x - tile * a.nplanes_fast;
+  }
+  const int iy0 = tile * R;
   const int f = tid / NT, u = tid - f * NT;
   T2 *row = s + f * PS;
   const int tws_n = a.tw_len / NX;  // stride for exp(-2 pi i k / Nx)
@@ -338,7 +348,12 @@ int launch_row_mode(RowArgs<T> &a, long long nplanes) {
   OX_REQUIRE(a.ny % R == 0, "ny must be a multiple of %d", R);
   auto k = fused_row_kernel<T, MX, R, MODE>;
   OX_TRY(set_smem(k, smem));
+  static const bool rows_fastest = [] { const char *e = getenv("ORPHX_KB_ORDER"); return e && !strcmp(e, "rows"); }();
   dim3 grid(a.ny / R, (unsigned)nplanes);
+  if (!rows_fastest && (long long)(a.ny / R) * nplanes < (1LL << 31)) {
+    a.nplanes_fast = (int)nplanes;
+    grid = dim3((unsigned)((a.ny / R) * nplanes), 1);
+  }
   const size_t wbytes = sizeof(T) * (size_t)a.ny * a.nx;
   if (a.window && a.win_group_stride == 0 && nplanes > 1 && l2_persist_budget() >= wbytes) {
     // the window is shared by every plane of the launch but is evicted from L2 between its uses by the

@@ -14,11 +14,11 @@ using namespace ox;
 namespace {
 
 // SUM[d] += sum_m x[m][d];  CROSS[i][j] += sum_m x[m][i] x[m][j]   (fixed m order)
-__global__ void stats_accumulate_kernel(const double *__restrict__ x, int nsim, int dim, long long *__restrict__ n,
-                                        double *__restrict__ sum, double *__restrict__ cross) {
+__global__ void stats_accumulate_kernel(const double *__restrict__ x, int nsim, int dim, double *__restrict__ packed) {
+  double *n = packed, *sum = packed + 1, *cross = packed + 1 + dim;
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)dim * dim;
-  if (t == 0) *n += nsim;
+  if (t == 0) *n += (double)nsim;
   if (t < dim) {
     double acc = sum[t];
     for (int m = 0; m < nsim; m++) acc += x[(long long)m * dim + t];
@@ -65,9 +65,7 @@ int ox_pipeline_create(ox_simplan *s, ox_powerplan *p, ox_binner *b, const doubl
     pl->has_window = true;
   }
   size_t d = pl->dim;
-  if ((st = pl->stat_n.ensure(sizeof(long long))) != OX_OK) return fail(st);
-  if ((st = pl->stat_sum.ensure(sizeof(double) * d)) != OX_OK) return fail(st);
-  if ((st = pl->stat_cross.ensure(sizeof(double) * d * d)) != OX_OK) return fail(st);
+  if ((st = pl->stat.ensure(sizeof(double) * (1 + d + d * d))) != OX_OK) return fail(st);
   if ((st = pl->bp.ensure(sizeof(double) * d * s->max_batch)) != OX_OK) return fail(st);
   // hand-written fused FFT path when the geometry allows it (ORPHX_PIPELINE=cufft|fused overrides)
   pl->path = 1;
@@ -93,17 +91,13 @@ int ox_pipeline_destroy(ox_pipeline *pl) {
 int ox_pipeline_stats_reset(ox_pipeline *pl) {
   OX_REQUIRE(pl, "null pipeline");
   size_t d = pl->dim;
-  OX_CUDA(cudaMemsetAsync(pl->stat_n.p, 0, sizeof(long long), g_stream));
-  OX_CUDA(cudaMemsetAsync(pl->stat_sum.p, 0, sizeof(double) * d, g_stream));
-  OX_CUDA(cudaMemsetAsync(pl->stat_cross.p, 0, sizeof(double) * d * d, g_stream));
+  OX_CUDA(cudaMemsetAsync(pl->stat.p, 0, sizeof(double) * (1 + d + d * d), g_stream));
   return OX_OK;
 }
 
-int ox_pipeline_stats(ox_pipeline *pl, long long **n_dev, double **sum_dev, double **cross_dev, int *dim) {
+int ox_pipeline_stats(ox_pipeline *pl, double **packed_dev, int *dim) {
   OX_REQUIRE(pl, "null pipeline");
-  if (n_dev) *n_dev = pl->stat_n.as<long long>();
-  if (sum_dev) *sum_dev = pl->stat_sum.as<double>();
-  if (cross_dev) *cross_dev = pl->stat_cross.as<double>();
+  if (packed_dev) *packed_dev = pl->stat.as<double>();
   if (dim) *dim = pl->dim;
   return OX_OK;
 }
@@ -120,10 +114,11 @@ static int pipeline_run_impl(ox_pipeline *pl, const long long *seeds, int nsim, 
     const double *noise_dev;
     OX_TRY(sim_stage_inputs(s, seeds, nsim, noise_mode, noise, noise_where, &noise_dev));
     OX_REQUIRE(!(flags & OX_FLAG_ROT) || s->ncomp == 3, "EB->QU rotation needs ncomp == 3");
-    OX_TRY(fused_run(pl, nsim, noise_mode, noise_dev, flags, (flags & OX_FLAG_KEEP_MAPS) != 0, ev));
+    pl->maps_valid = (flags & OX_FLAG_KEEP_MAPS) != 0;
+    OX_TRY(fused_run(pl, nsim, noise_mode, noise_dev, flags, pl->maps_valid, ev));
     long long total2 = (long long)pl->dim * pl->dim;
     stats_accumulate_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, g_stream>>>(
-        pl->bp.as<double>(), nsim, pl->dim, pl->stat_n.as<long long>(), pl->stat_sum.as<double>(), pl->stat_cross.as<double>());
+        pl->bp.as<double>(), nsim, pl->dim, pl->stat.as<double>());
     OX_KERNEL_CHECK();
     if (ev) OX_CUDA(cudaEventRecord(ev[6], g_stream));
     if (bandpowers) OX_TRY(stage_out(bandpowers, out_where, pl->bp.p, sizeof(double) * (size_t)nsim * pl->dim));
@@ -131,6 +126,7 @@ static int pipeline_run_impl(ox_pipeline *pl, const long long *seeds, int nsim, 
   }
 #define OX_MARK(i) do { if (ev) OX_CUDA(cudaEventRecord(ev[i], g_stream)); } while (0)
   OX_MARK(0);
+  pl->maps_valid = true;
   // 1. k_h = Hermitian part of covsqrt.noise / sqrt(Npix)          (hand-written)
   OX_TRY(sim_fill_half(s, seeds, nsim, noise_mode, noise, noise_where, flags));
   OX_MARK(1);
@@ -152,7 +148,7 @@ static int pipeline_run_impl(ox_pipeline *pl, const long long *seeds, int nsim, 
   // 6. Statistics triple
   long long total = (long long)pl->dim * pl->dim;
   stats_accumulate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g_stream>>>(
-      pl->bp.as<double>(), nsim, pl->dim, pl->stat_n.as<long long>(), pl->stat_sum.as<double>(), pl->stat_cross.as<double>());
+      pl->bp.as<double>(), nsim, pl->dim, pl->stat.as<double>());
   OX_KERNEL_CHECK();
   OX_MARK(6);
 #undef OX_MARK
@@ -173,7 +169,7 @@ int ox_pipeline_path(ox_pipeline *pl, int *path) {
 
 int ox_pipeline_maps(ox_pipeline *pl, void **maps_dev) {
   OX_REQUIRE(pl && maps_dev, "null pointer");
-  *maps_dev = pl->s->maps.p;
+  *maps_dev = pl->maps_valid ? pl->s->maps.p : nullptr;  // null: the last (fused) run did not keep them
   return OX_OK;
 }
 

@@ -31,8 +31,10 @@ struct ox_qeplan {
   DevBuf kx, ky;           // staged inputs (half or full plane complex)
   DevBuf in_real;          // staged real maps
   DevBuf legs, fields, prod, pk, khat, full, full2, out_real;
-  DevBuf mf;               // double2 [ny][nxh] mean-field accumulator of kappa_hat(l)
-  DevBuf mf_count;         // int64
+  // mean-field accumulator packed for ONE all-reduce (Statistics.add_stack, stats.py:1227-1228):
+  // float64 [2 * ny * nxh (the complex128 sum of kappa_hat(l) on the half plane) | count | pad]
+  DevBuf mf;
+  double *mf_count() const { return mf.as<double>() + 2 * (size_t)g->ny * g->nxh; }
   // hand-written FFT path (TT on half planes, power-of-two maps): tables and intermediates in the
   // transposed half-plane layout [plane][ix][iy] of ox_fused_kernels.cuh
   bool fused = false;
@@ -516,9 +518,11 @@ int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, i
       ra.ny = ny; ra.nx = nx; ra.mx = nx / 2;
       ra.map_in_group_stride = n;
       OX_TRY(oxk::launch_row_any<T>(ra, nb, QeRowModes()));                                            // Q1
+      stage_mark("Q1 rows r2c");
       ColPlainOps<T> op{q->Hx.as<T2>(), K, ny, nxh, 1.0};
       OX_COL_DISPATCH(T, -1, op, q->tw.p, q->tw_len, nxh, nb, ny, st);                   // Q2a
       OX_TRY(st);
+      stage_mark("Q2a cols fwd");
     }
   }
   // ---- legs -> real fields -> products
@@ -530,6 +534,7 @@ int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, i
     LegsOps<T> op{q->Kx.as<T2>(), two ? q->Ky.as<T2>() : q->Kx.as<T2>(), q->legT.as<T>(), lx, q->Lt.as<T2>(), ny, nxh, nb, nl};
     OX_COL_DISPATCH(T, +1, op, q->tw.p, q->tw_len, nxh, (long long)nl * nb, ny, st);     // Q2b
     OX_TRY(st);
+    stage_mark("Q2b legs cols inv");
   }
   {
     oxk::RowArgs<T> ra;
@@ -542,6 +547,7 @@ int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, i
     ra.tw_len = q->tw_len;
     ra.ny = ny; ra.nx = nx; ra.mx = nx / 2;
     OX_TRY(oxk::launch_row_any<T>(ra, (long long)nl * nb, QeRowModes()));                              // Q3a
+    stage_mark("Q3a rows c2r");
     ra.Hin = nullptr;
     ra.map_out = nullptr;
     ra.Hout = q->Pt.as<T2>();
@@ -560,11 +566,13 @@ int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, i
       ra.window2 = q->fields.as<T>() + 5 * n;
     }
     OX_TRY(oxk::launch_row_any<T>(ra, 2LL * nb, QeRowModes()));                                        // Q3b
+    stage_mark("Q3b product rows r2c");
   }
   {
     ColPlainOps<T> op{q->Pt.as<T2>(), q->Pt.as<T2>(), ny, nxh, 1.0};   // in place: a CTA owns its column
     OX_COL_DISPATCH(T, -1, op, q->tw.p, q->tw_len, nxh, 2LL * nb, ny, st);               // Q4
     OX_TRY(st);
+    stage_mark("Q4 cols fwd");
   }
   // ---- outputs
   double2 *mf = accumulate ? q->mf.as<double2>() : nullptr;
@@ -580,6 +588,7 @@ int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, i
     }
     qe_finish_kernel<T, T2><<<fgrid, tb, 0, g_stream>>>(q->Pt.as<T2>(), q->norm.as<T>(), ly, lx, ny, nx, nxh, nb, fullp, mf);
     OX_KERNEL_CHECK();
+    stage_mark("finish div+meanfield");
     if (return_ft) {
       if (out_where == OX_HOST) OX_TRY(stage_out(out, OX_HOST, fullp, sizeof(T2) * (size_t)nb * n));
       return OX_OK;
@@ -605,6 +614,7 @@ int reconstruct_fused_T(ox_qeplan *q, const void *x, const void *y, int where, i
     ra.tw_len = q->tw_len;
     ra.ny = ny; ra.nx = nx; ra.mx = nx / 2;
     OX_TRY(oxk::launch_row_any<T>(ra, nb, QeRowModes()));
+    stage_mark("kappa map (div, cols inv, rows c2r)");
   }
   return stage_out(out, out_where, q->out_real.p, sizeof(T) * (size_t)nb * n);
 }
@@ -743,7 +753,7 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
   return stage_out(out, out_where, q->out_real.p, bytes);
 }
 
-__global__ void add_count_kernel(long long *c, long long v) { *c += v; }
+__global__ void add_count_kernel(double *c, double v) { *c += v; }
 
 template <typename T>
 int upload_tables(ox_qeplan *q, const double *wxy, const double *wy, const double *norm, int where) {
@@ -829,8 +839,7 @@ int ox_qeplan_create(ox_geometry *g, int est, const double *wxy, const double *w
   }
   int st = dtype == OX_F64 ? upload_tables<double>(q, wxy, wy, norm, where) : upload_tables<float>(q, wxy, wy, norm, where);
   if (st == OX_OK && q->fused) st = dtype == OX_F64 ? make_leg_tables<double>(q) : make_leg_tables<float>(q);
-  if (st == OX_OK) st = q->mf.ensure(sizeof(double2) * (size_t)g->ny * g->nxh);
-  if (st == OX_OK) st = q->mf_count.ensure(sizeof(long long));
+  if (st == OX_OK) st = q->mf.ensure(sizeof(double2) * ((size_t)g->ny * g->nxh + 1));
   if (st != OX_OK) {
     delete q;
     return st;
@@ -846,8 +855,7 @@ int ox_qeplan_destroy(ox_qeplan *q) {
 
 int ox_qe_meanfield_reset(ox_qeplan *q) {
   OX_REQUIRE(q, "null plan");
-  OX_CUDA(cudaMemsetAsync(q->mf.p, 0, sizeof(double2) * (size_t)q->g->ny * q->g->nxh, g_stream));
-  OX_CUDA(cudaMemsetAsync(q->mf_count.p, 0, sizeof(long long), g_stream));
+  OX_CUDA(cudaMemsetAsync(q->mf.p, 0, sizeof(double2) * ((size_t)q->g->ny * q->g->nxh + 1), g_stream));
   return OX_OK;
 }
 
@@ -857,12 +865,16 @@ int ox_qe_path(ox_qeplan *q) {
   return (q->real_path && q->est == OX_QE_TT) ? 1 : 0;
 }
 
-int ox_qe_meanfield(ox_qeplan *q, void **accum_dev, long long **count_dev, long long *nelem) {
+int ox_qe_meanfield(ox_qeplan *q, double **packed_dev, long long *nelem) {
   OX_REQUIRE(q, "null plan");
-  if (accum_dev) *accum_dev = q->mf.p;
-  if (count_dev) *count_dev = q->mf_count.as<long long>();
+  if (packed_dev) *packed_dev = q->mf.as<double>();
   if (nelem) *nelem = (long long)q->g->ny * q->g->nxh;
   return OX_OK;
+}
+
+int ox_qe_meanfield_allreduce(ox_comm *c, ox_qeplan *q) {
+  OX_REQUIRE(c && q, "null pointer");
+  return comm_allreduce_f64(c, q->mf.as<double>(), 2 * (long long)q->g->ny * q->g->nxh + 1);   // [stack | count]
 }
 
 int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int nbatch, int already_ft, int return_ft,
@@ -874,7 +886,7 @@ int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int
                ? reconstruct_T<double, double2>(q, x, y, where, nbatch, already_ft, return_ft, accumulate_meanfield, kappa_out, out_where)
                : reconstruct_T<float, float2>(q, x, y, where, nbatch, already_ft, return_ft, accumulate_meanfield, kappa_out, out_where);
   if (st == OX_OK && accumulate_meanfield) {
-    add_count_kernel<<<1, 1, 0, g_stream>>>(q->mf_count.as<long long>(), (long long)nbatch);
+    add_count_kernel<<<1, 1, 0, g_stream>>>(q->mf_count(), (double)nbatch);
     OX_KERNEL_CHECK();
   }
   return st;

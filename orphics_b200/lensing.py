@@ -210,21 +210,25 @@ class qest(object):
 
     def meanfield(self, XY):
         """(sum of kappa_hat(l) on the half plane, count) accumulated on the device."""
-        h, _ = self._plans[XY]
-        p, c, n = C.c_void_p(), C.c_void_p(), C.c_longlong()
-        check(lib.ox_qe_meanfield(h, C.byref(p), C.byref(c), C.byref(n)))
+        p, nel = self.meanfield_pointer(XY)
         ny, nx = self.geometry.shape
-        acc = np.empty((ny, nx // 2 + 1), dtype=np.complex128)
-        cnt = np.empty(1, dtype=np.int64)
-        check(lib.ox_memcpy_d2h(ptr(acc), p, acc.nbytes))
-        check(lib.ox_memcpy_d2h(ptr(cnt), c, 8))
-        return acc, int(cnt[0])
+        packed = np.empty(2 * nel + 1, dtype=np.float64)
+        check(lib.ox_memcpy_d2h(ptr(packed), C.c_void_p(p), packed.nbytes))
+        acc = packed[:2 * nel].view(np.complex128).reshape(ny, nx // 2 + 1).copy()
+        return acc, int(round(packed[2 * nel]))
 
-    def meanfield_pointers(self, XY):
+    def meanfield_pointer(self, XY):
+        """Device address of the packed float64 [stack (complex128 half plane) | count] and the stack's
+        number of complex elements."""
         h, _ = self._plans[XY]
-        p, c, n = C.c_void_p(), C.c_void_p(), C.c_longlong()
-        check(lib.ox_qe_meanfield(h, C.byref(p), C.byref(c), C.byref(n)))
-        return p.value, c.value, int(n.value)
+        p, n = C.c_void_p(), C.c_longlong()
+        check(lib.ox_qe_meanfield(h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def allreduce_meanfield(self, XY, comm):
+        """Sum the mean-field stack and its count over the ranks of an mpi.Comm: ONE ncclAllReduce
+        (Statistics.add_stack / allreduce, stats.py:1227-1228)."""
+        check(lib.ox_qe_meanfield_allreduce(comm.handle, self._plans[XY][0]))
 
     def reset_meanfield(self, XY):
         check(lib.ox_qe_meanfield_reset(self._plans[XY][0]))
@@ -340,11 +344,14 @@ class _C2C(object):
 
 
 def kappa_to_phi(kappa, modlmap, return_fphi=False, _fft=None):
-    """lensing.py:651-657 (enmap.fft/ifft with normalize='phys': the pixel-area factors cancel)."""
+    """lensing.py:651-657.  The reference transforms with enmap.fft/ifft(normalize='phys'): forward = raw FFT x
+    (pixsize/Npix)^1/2, backward = raw backward FFT / (pixsize Npix)^1/2.  The factors cancel in phi, but the
+    returned fphi carries the forward one."""
     g = Geometry.get(kappa.shape, kappa.wcs)
     f = _fft or _C2C(g)
-    fphi = fkappa_to_fphi(f(np.asarray(kappa)), modlmap)
-    phi = ndmap(f(fphi, inverse=True).real, kappa.wcs)
+    pix = _enmap.pixsize(g.shape, kappa.wcs, method=g.method)
+    fphi = fkappa_to_fphi(f(np.asarray(kappa), scale=float(np.sqrt(pix / g.npix))), modlmap)
+    phi = ndmap(f(fphi, inverse=True, scale=float(1.0 / np.sqrt(pix * g.npix))).real, kappa.wcs)
     return (phi, ndmap(fphi, kappa.wcs)) if return_fphi else phi
 
 

@@ -88,10 +88,18 @@ def multi_pow(mat, exp):
     return out
 
 
+try:                                   # 1-D host set-up only (the per-pixel work is on the device)
+    import scipy.fft as _fft1d
+except ImportError:                    # pragma: no cover
+    _fft1d = np.fft
+
+
 def _sym_convolve(a, b):
+    # C_l l^2 spans ~10 decades, so two FFT libraries agree on this convolution only to ~1e-9 of the peak;
+    # scipy.fft (pocketfft, what the oracle uses) keeps the set-up reproducible to rounding
     sa = np.concatenate([a, a[:, -2:0:-1]], -1)
     sb = np.concatenate([b, b[:, -2:0:-1]], -1)
-    out = np.fft.irfft(np.fft.rfft(sa, axis=-1) * np.fft.rfft(sb, axis=-1), n=sa.shape[-1], axis=-1)
+    out = _fft1d.irfft(_fft1d.rfft(sa, axis=-1) * _fft1d.rfft(sb, axis=-1), n=sa.shape[-1], axis=-1)
     return out[:, :a.shape[-1]]
 
 
@@ -408,7 +416,8 @@ class FourierCalc(object):
         out = np.empty((nb, ns, binner.centers.size), dtype=np.float64)
         flags = self._flags(rot=rot and nc == 3, pixel_units=pixel_units, skip_cross=skip_cross)
         check(lib.ox_power_bin(self._plan(nc, nb), binner.handle, ptr(s1), ptr(s2), OX_HOST, nb, flags, ptr(w), OX_HOST, ptr(out), OX_HOST))
-        return out
+        # bin2D's short-bincount quirk (stats.py:796-797): same length as binner.bin() returns
+        return out[..., :binner.trimmed_nbins]
 
     def __del__(self):
         try:
@@ -630,6 +639,8 @@ class SimPipeline(object):
         keep_maps=True on the fused path)."""
         p = C.c_void_p()
         check(lib.ox_pipeline_maps(self.handle, C.byref(p)))
+        if not p.value:
+            raise RuntimeError("last_maps: the last run did not keep its real-space maps (fused path: pass keep_maps=True)")
         mg = self.mapgen
         out = np.empty((nsim, mg.ncomp) + mg.geometry.shape, dtype=_capi.np_dtype(mg.dtype))
         check(lib.ox_memcpy_d2h(ptr(out), p, out.nbytes))
@@ -665,7 +676,9 @@ class SimPipeline(object):
             check(lib.ox_pipeline_run(self.handle, ptr(s64), n, mode, ptr(nz), OX_HOST, flags,
                                       ptr(dst) if fetch else None, OX_HOST))
             done += n
-        return res if fetch else None
+        # bin2D's short-bincount quirk (stats.py:796-797): the bandpowers handed back have the length
+        # binner.bin() returns; the device Statistics triple keeps the full nbins-long vectors
+        return res[..., :self.binner.trimmed_nbins] if fetch else None
 
     def run_raw(self, seeds_i64, nsim, mode, flags, out_ptr):
         """Thin call for benchmarks: seeds_i64 is a contiguous int64 numpy array (e.g. pinned)."""
@@ -679,22 +692,23 @@ class SimPipeline(object):
         check(lib.ox_pipeline_profile(self.handle, ptr(seeds_i64), nsim, mode, flags, ms))
         return dict(zip(self.STAGES, [float(v) for v in ms]))
 
-    def stats_pointers(self):
-        n, s, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    def stats_pointer(self):
+        """Device address of the packed float64 [N | SUM[dim] | CROSS[dim][dim]] accumulator and dim."""
+        p = C.c_void_p()
         d = C.c_int()
-        check(lib.ox_pipeline_stats(self.handle, C.byref(n), C.byref(s), C.byref(c), C.byref(d)))
-        return n.value, s.value, c.value, d.value
+        check(lib.ox_pipeline_stats(self.handle, C.byref(p), C.byref(d)))
+        return p.value, d.value
 
     def stats(self):
         """(N, SUM, CROSS) accumulated on the device so far."""
-        n, s, c, d = self.stats_pointers()
-        N = np.empty(1, dtype=np.int64)
-        S = np.empty(d, dtype=np.float64)
-        Cm = np.empty((d, d), dtype=np.float64)
-        check(lib.ox_memcpy_d2h(ptr(N), C.c_void_p(n), 8))
-        check(lib.ox_memcpy_d2h(ptr(S), C.c_void_p(s), 8 * d))
-        check(lib.ox_memcpy_d2h(ptr(Cm), C.c_void_p(c), 8 * d * d))
-        return int(N[0]), S, Cm
+        p, d = self.stats_pointer()
+        packed = np.empty(1 + d + d * d, dtype=np.float64)
+        check(lib.ox_memcpy_d2h(ptr(packed), C.c_void_p(p), packed.nbytes))
+        return int(round(packed[0])), packed[1:1 + d].copy(), packed[1 + d:].reshape(d, d).copy()
+
+    def allreduce(self, comm):
+        """Sum the Statistics triple over the ranks of an mpi.Comm: ONE ncclAllReduce (stats.py:1215-1217)."""
+        check(lib.ox_pipeline_allreduce(comm.handle, self.handle))
 
     def reset_stats(self):
         check(lib.ox_pipeline_stats_reset(self.handle))

@@ -78,3 +78,62 @@ def distribute(njobs, verbose=True, **kwargs):
     if rank == 0 and verbose:
         print("At most ", max(num_each), " tasks...")
     return comm, rank, each_tasks[rank]
+
+
+class NcclComm:
+    """Communicator of the C ABI (ox_comm_*, include/orphx.h): the data plane of the one exchange step of the
+    path -- Statistics.allreduce (stats.py:1184-1232) -- as ncclAllReduce(sum) over NVLink issued by
+    liborphx.so on its own stream.  torch.distributed (or any other rendezvous) is only used to hand rank 0's
+    128-byte NCCL unique id to the other ranks.  With one rank no NCCL is needed and reductions are no-ops."""
+
+    def __init__(self, rank=0, nranks=1, group=None, unique_id=None):
+        import ctypes as C
+        from ._capi import lib, check, ptr, require_device
+        require_device()
+        self.rank, self.nranks = int(rank), int(nranks)
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.nranks > 1:
+            if unique_id is not None:
+                uid[:] = np.frombuffer(bytes(unique_id), dtype=np.uint8)[:128]
+            else:
+                import torch.distributed as dist
+                if self.rank == 0:
+                    check(lib.ox_comm_unique_id(ptr(uid), uid.nbytes))
+                box = [uid.tobytes()]
+                dist.broadcast_object_list(box, src=0, group=group)
+                uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+        h = C.c_void_p()
+        check(lib.ox_comm_create(self.rank, self.nranks, ptr(uid), uid.nbytes, C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def new_unique_id():
+        from ._capi import lib, check, ptr
+        uid = np.zeros(128, dtype=np.uint8)
+        check(lib.ox_comm_unique_id(ptr(uid), uid.nbytes))
+        return uid.tobytes()
+
+    def nccl_version(self):
+        import ctypes as C
+        from ._capi import lib, check
+        r, n, v = C.c_int(), C.c_int(), C.c_int()
+        check(lib.ox_comm_info(self.handle, C.byref(r), C.byref(n), C.byref(v)))
+        return v.value
+
+    def allreduce_f64(self, dev_ptr, count):
+        """In-place sum of count float64 values at a device address."""
+        import ctypes as C
+        from ._capi import lib, check
+        check(lib.ox_comm_allreduce_f64(self.handle, C.c_void_p(int(dev_ptr)), int(count)))
+
+    def free(self):
+        from ._capi import lib
+        if getattr(self, "handle", None):
+            lib.ox_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

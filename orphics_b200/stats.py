@@ -32,6 +32,13 @@ class bin2D(object):
         h = C.c_void_p()
         if geometry is not None:
             self._n = geometry.npix
+            # the slot index is derived on the device from the geometry's own |l|: refuse any other modrmap
+            # (a real-space radius map, a masked or edited modlmap) instead of silently binning by |l|
+            if modrmap is not None:
+                m = np.asarray(modrmap)
+                if m.shape != tuple(geometry.shape) or not np.array_equal(m, geometry.modlmap()):
+                    raise ValueError("bin2D(geometry=...): modrmap must be the geometry's modlmap(); "
+                                     "drop geometry= to bin by an arbitrary modrmap")
             check(lib.ox_binner_create_geom(geometry.handle, ptr(self._edges64), self._edges64.size, C.byref(h)))
         else:
             m = np.ascontiguousarray(np.asarray(modrmap), dtype=np.float64)
@@ -44,6 +51,10 @@ class bin2D(object):
         cnt = np.empty(self.nslots, dtype=np.int64)
         check(lib.ox_binner_counts(self.handle, ptr(cnt)))
         self.slot_counts = cnt  # == np.bincount(digitized, minlength=len(edges)+1)
+        #: number of bandpowers the reference returns: np.bincount(digitized)[1:-1] is only max(digitized)+1 long
+        #: (stats.py:796-797), so when no pixel lies above the last edge the last occupied bin is trimmed too.
+        #: The fixed-shape fused outputs (binned_power_batch, SimPipeline) are cut to this length on the host.
+        self.trimmed_nbins = int(self._trim(cnt, cnt).size)
 
     @property
     def digitized(self):
@@ -56,7 +67,9 @@ class bin2D(object):
 
     def _raw(self, data, weights, flags):
         data = np.asarray(data)
-        dt = _capi.OX_F32 if data.dtype == np.float32 else _capi.OX_F64
+        # float32 data stay float32 on the device unless weights are given: the reference's weights are float64
+        # (np.bincount promotes), so weighted sums are formed in float64
+        dt = _capi.OX_F32 if (data.dtype == np.float32 and weights is None) else _capi.OX_F64
         d = np.ascontiguousarray(data, dtype=_capi.np_dtype(dt))
         if d.size % self._n != 0:
             raise ValueError(f"data size {d.size} is not a multiple of the binner's {self._n} pixels")
