@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: maps/sec through sim -> FFT -> power2d -> bin2D at
-2048^2 fp64 (BASELINE.json metric; workload = configs[1], T-only GRF sims from the CAMB
+2048^2 fp64 (BASELINE.json metric; headline workload = configs[1], T-only GRF sims from the CAMB
 lensed TT spectrum at 0.5 arcmin, 72 bandpowers), one process per GPU.
 
   python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, liborphx.so)
@@ -11,14 +11,20 @@ pipeline is three hand-written kernels (orphics_b200/csrc/ox_fused.cu):
   K_A Philox noise x covsqrt -> inverse FFT along y        (writes the transposed half plane)
   K_B inverse FFT along x -> real map (stored) x taper -> forward FFT along x
   K_C forward FFT along y -> |k|^2 -> deterministic annular binning -> bandpowers
-followed by the Statistics triple; other sizes use cuFFT passes with hand-written kernels
-around them (ORPHX_PIPELINE=cufft forces that path).
-Prints ONE JSON line on rank 0.
+followed by the Statistics triple; at the end the packed [N | SUM | CROSS] is summed over the ranks
+with ONE ncclAllReduce issued by liborphx.so (ox_pipeline_allreduce).  torch.distributed is only the
+rendezvous (NCCL unique id, barrier, max over ranks of the timings).
+
+The JSON line also carries a "configs" block with the other BASELINE configurations measured the same
+way (value, e2e, roofline of the dominant kernel, cpu_baseline):
+  configs[2]  IQU 2048^2 with the TEB rotation, 6 binned spectra
+  configs[3]  TT quadratic estimator on 4096^2 maps, 512 realisations sharded over the GPUs + mean-field all-reduce
+  configs[4]  EB quadratic estimator at 8192^2, fp64 and fp32
+(--configs none skips them, --configs 2,3 selects).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -29,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 EDGES = np.arange(100, 3000, 40.0)      # tutorials/demo-grf.ipynb:159
+KEDGES = np.linspace(20, 3500, 20)      # tutorials/tt_verification.ipynb:600
 SEED0 = 1000                            # sim i uses seed 1000+i
 METRIC = "maps/sec sim->FFT->power2d->bin2D at 2048^2 fp64"
 
@@ -36,7 +43,7 @@ METRIC = "maps/sec sim->FFT->power2d->bin2D at 2048^2 fp64"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128, help="timed steps (128 x 64 maps ~ 0.7 s on one B200)")
+    ap.add_argument("--steps", type=int, default=128, help="timed steps (128 x 64 maps ~ 0.5 s on one B200)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="maps per step per GPU")
@@ -47,57 +54,83 @@ def parse():
                     help="philox_hermitian draws the Hermitian half plane directly (N normals per map); "
                          "philox draws the reference's full complex plane (4N normals per map)")
     ap.add_argument("--no-keep-maps", action="store_true", help="do not store the real-space maps in HBM")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
-    ap.add_argument("--pol", action="store_true", help="IQU sims, 6 spectra (configs[2])")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (variants, per-call API)")
+    ap.add_argument("--pol", action="store_true", help="headline workload = IQU sims, 6 spectra (configs[2])")
     ap.add_argument("--no-window", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=24, help="maps timed for cpu_baseline: ~10 s on one host core (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--configs", default="all", help="'all', 'none' or a list out of 2,3,4: the other BASELINE configs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --steps x --batch maps per GPU; strong: --total maps shared by the GPUs (configs[1] literal)")
+    ap.add_argument("--total", type=int, default=1024, help="maps of the whole job under --scaling strong")
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU sampled through NVML from a thread of this process every
+    ~4 ms while the timed region runs (nvidia-smi's own loop is too coarse for a 70 ms region)."""
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+               ("hw_power_brake", 0x80), ("sync_boost", 0x10))
+
+    def __init__(self, gpu_index, period=0.004):
+        self.rows, self.gpu, self.period, self.h, self.err = [], gpu_index, period, None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except Exception:
+                    idx = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:           # noqa: BLE001
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(sm), float(pw), int(rs)))
+            except Exception as e:       # noqa: BLE001
+                self.err = repr(e)
+                break
+            self._stop.wait(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, power, reasons = [], [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "power_w_max": float(max(power)), "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)], "samples": 0}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"], "samples": 0}
+        sm = np.array([r[0] for r in self.rows])
+        pw = np.array([r[1] for r in self.rows])
+        bits = 0
+        busy = np.ones(len(sm), dtype=bool)      # the sampler only runs inside the timed region: every sample is under load
+        for r, b in zip(self.rows, busy):
+            if b:
+                bits |= r[2] & ~0x1              # (bit 0 = "GPU idle", not a throttle reason)
+        reasons = [name for name, bit in self.REASONS if bits & bit]
+        return {"sm_mhz": float(np.median(sm[busy])), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "power_w_max": float(pw.max()), "samples": int(len(sm)), "samples_under_load": int(busy.sum())}
 
 
 # --------------------------------------------------------------------------- CPU reference path (oracle)
@@ -127,53 +160,59 @@ def _oracle_one(seed):
     return o["b"].bin(p2d)[1]
 
 
-def cpu_baseline_sample(args, nmaps):
+def cpu_baseline_sample(npix, res, pol, window, nmaps):
     """1 core, nmaps maps of the same workload (set-up excluded, 1 warm-up map)."""
-    _oracle_setup(args.npix, args.res, args.pol, not args.no_window)
+    _oracle_setup(npix, res, pol, window)
     _oracle_one(SEED0)
     t0 = time.perf_counter()
     for i in range(nmaps):
         _oracle_one(SEED0 + i)
     dt = time.perf_counter() - t0
     return {"value": nmaps / dt, "unit": "maps/s", "cores": 1, "kind": "port",
-            "sample": f"{nmaps} maps of {args.npix}^2 {'IQU' if args.pol else 'T'} through the numpy oracle "
-                      f"(MapGen.get_map -> taper -> power2d -> bin2D.bin), 1 process / 1 thread, set-up excluded"}
+            "sample": f"{nmaps} maps of {npix}^2 {'IQU' if pol else 'T'} through the numpy oracle "
+                      f"(MapGen.get_map [numpy MT19937 full-plane noise] -> taper -> power2d -> bin2D.bin), 1 process / 1 thread, set-up excluded"}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (numpy oracle; the reference
     itself cannot be imported: pixell is absent) on all host cores, one process per core
-    with realisations split as the reference does under MPI (mpi.py:78-91)."""
+    with realisations split as the reference does under MPI (mpi.py:78-91).  A step is the same
+    --batch maps as the GPU arm's step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    ncpu = os.cpu_count() or 1
-    try:
-        ncpu = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
+    ncpu = host_cores()
     mem_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 2 ** 30
     per_proc_gb = 1.5 * (args.npix / 2048.0) ** 2 * (3 if args.pol else 1)
-    P = max(1, int(min(ncpu, 64, mem_gb * 0.5 / per_proc_gb)))
+    P = max(1, int(min(ncpu, 64, args.batch, mem_gb * 0.5 / per_proc_gb)))
     ctx = mp.get_context("fork")
     window = not args.no_window
     with ctx.Pool(P, initializer=_oracle_setup, initargs=(args.npix, args.res, args.pol, window)) as pool:
-        step_maps = P                                             # one map per core per step
+        step_maps = args.batch
         for w in range(args.warmup):
-            pool.map(_oracle_one, [SEED0 + i for i in range(step_maps)], chunksize=1)
+            pool.map(_oracle_one, [SEED0 + i for i in range(P)], chunksize=1)      # warm-up: one map per process
         t0 = time.perf_counter()
         for k in range(args.steps):
             pool.map(_oracle_one, [SEED0 + k * step_maps + i for i in range(step_maps)], chunksize=1)
         dt = time.perf_counter() - t0
     value = args.steps * step_maps / dt
-    sample = (f"{step_maps} maps per step ({P} processes x 1 map, 1 FFT thread each) of {args.npix}^2 "
+    sample = (f"{step_maps} maps per step over {P} processes (1 FFT thread each) of {args.npix}^2 "
               f"{'IQU' if args.pol else 'T'}; numpy-oracle restatement of MapGen.get_map -> taper -> power2d -> bin2D.bin")
+    cfg = workload_config(args, step_maps, 1)
+    cfg["noise"] = "numpy MT19937 full complex plane (np.random.seed + rand_gauss_harm, maps.py:1577-1578)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, step_maps, 1),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "maps/s", "cores": P, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -188,250 +227,519 @@ def workload_config(args, batch, ngpu):
             "maps_per_step_per_gpu": batch, "global_batch": batch * ngpu, "npix": args.npix, "ncomp": 3 if args.pol else 1,
             "nbins": len(EDGES) - 1, "noise": args.noise, "window": not args.no_window,
             "maps_materialised_in_hbm": not args.no_keep_maps,
-            "parallelism": f"realisations sharded over {ngpu} GPU(s) (mpi_distribute rule), one all-reduce of the Statistics triple",
+            "parallelism": f"realisations sharded over {ngpu} GPU(s) (mpi_distribute rule), one ncclAllReduce of the packed Statistics triple",
             "l2": "working set per step (batch x 67 MB of maps+Fourier planes) >> 126 MB L2; no flush needed"}
 
 
 # --------------------------------------------------------------------------- this repo
-class _DevView:
-    """__cuda_array_interface__ holder so torch can wrap a liborphx device buffer in place."""
+class Ctx:
+    """Per-process state shared by the measurements: rank, communicator, peak, timing helpers."""
 
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+    def __init__(self):
+        from orphics_b200 import _capi, mpi
+        self.capi, self.mpi = _capi, mpi
+        self.rank, self.local, self.ws = mpi.init_process_group()
+        self.dist = self.torch = None
+        if self.ws > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+        _capi.require_device()
+        _capi.set_device(self.local)
+        self.comm = mpi.NcclComm(self.rank, self.ws)     # data plane: ncclAllReduce issued by liborphx.so
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.peak_src = ("MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks
+                         else "B200_PROFILING.md fallback 6650 GB/s (of fallback)")
+        self.traffic = {}
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+            self.traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        except Exception:
+            pass
+
+    def barrier(self):
+        self.capi.synchronize()
+        if self.ws > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.ws == 1:
+            return float(v)
+        t = self.torch.tensor([v], device=f"cuda:{self.local}", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, step, nsteps, finish=None):
+        """Device time (CUDA events on the library stream) of nsteps calls of step(k) [+ finish()], bracketed by a
+        barrier + synchronize on both sides; max over ranks.  Returns (ms, launches)."""
+        self.barrier()
+        tm = self.capi.Timer()
+        l0 = self.capi.launch_count()
+        tm.start()
+        for k in range(nsteps):
+            step(k)
+        if finish is not None:
+            finish()
+        tm.stop()
+        ms = tm.elapsed_ms()
+        launches = self.capi.launch_count() - l0
+        self.barrier()
+        return self.max_over_ranks(ms), launches
+
+    def wall(self, step, nsteps, finish=None):
+        """Wall-clock seconds of nsteps host-facing calls (each synchronises on its own D2H); max over ranks."""
+        self.barrier()
+        t0 = time.perf_counter()
+        for k in range(nsteps):
+            step(k)
+        if finish is not None:
+            finish()
+        self.capi.synchronize()
+        dt = time.perf_counter() - t0
+        self.barrier()
+        return self.max_over_ranks(dt)
+
+    def roofline(self, stage_ms, alg_bytes, key, note=None):
+        """roofline object of the dominant stage: achieved = algorithmic bytes per launch / its CUDA-event time."""
+        dom = max((k for k in stage_ms if alg_bytes.get(k)), key=lambda k: stage_ms[k])
+        gbs = alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        tr = self.traffic.get(key, {}).get(dom)
+        r = {"bound": "hbm", "kernel": dom, "achieved": gbs, "peak": self.peak, "unit": "GB/s", "frac": gbs / self.peak,
+             "traffic": tr, "peak_source": self.peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom],
+             "ms_per_launch": stage_ms[dom]}
+        if tr:
+            r["traffic_over_algorithmic"] = tr / alg_bytes[dom]
+        if note:
+            r["note"] = note
+        return r
+
+    def stages(self, stage_ms, alg_bytes):
+        out = {}
+        for k, ms in stage_ms.items():
+            b = alg_bytes.get(k)
+            gbs = b / (ms * 1e-3) / 1e9 if (b and ms > 0) else None
+            out[k] = {"ms_per_launch": ms, "algorithmic_bytes_per_launch": b, "achieved_gbs": gbs,
+                      "frac": gbs / self.peak if gbs else None}
+        return out
 
 
-def run_ours(args):
-    from orphics_b200 import _capi, maps, stats, mpi, cosmology
-    rank, local, ws = mpi.init_process_group()
-    dist = torch = None
-    if ws > 1:
-        import torch
-        import torch.distributed as dist
-    _capi.require_device()
-    _capi.set_device(local)
-    npix, B, K, W = args.npix, args.batch, args.steps, args.warmup
-    pol = args.pol
-    dtype = np.float32 if args.dtype == "f32" else np.float64
+def profile_stages(capi, fn, reps=3):
+    """Average per-stage device times (ms) of fn() from the library's stage marks."""
+    acc = {}
+    for _ in range(reps):
+        with capi.StageProfile() as p:
+            fn()
+        for k, v in p.totals().items():
+            acc[k] = acc.get(k, 0.0) + v / reps
+    return acc
+
+
+def build_pipeline(args, npix, pol, B, dtype, noise):
+    from orphics_b200 import maps, stats, cosmology
     shape, wcs = maps.rect_geometry(width_arcmin=npix * args.res, px_res_arcmin=args.res, pol=pol)
     th = cosmology.default_theory()
     g = maps.Geometry.get(shape, wcs)
     modl = g.modlmap()
     ps = cosmology.power_from_theory(np.arange(0, modl.max() + 1, 1.0), th, lensed=True, pol=pol)
-    mg = maps.MapGen(shape, wcs, ps, noise=args.noise, dtype=dtype, max_batch=B)
+    mg = maps.MapGen(shape, wcs, ps, noise=noise, dtype=dtype, max_batch=B)
     fc = maps.FourierCalc(shape, wcs, dtype=dtype, max_batch=B)
     binner = stats.bin2D(modl, EDGES, geometry=g)
     window = None if args.no_window else np.asarray(maps.get_taper(shape, wcs)[0])
     pipe = maps.SimPipeline(mg, fc, binner, window=window)
-    mode = _capi.NOISE_MODES[args.noise]
+    return dict(shape=shape, wcs=wcs, th=th, g=g, ps=ps, mg=mg, fc=fc, binner=binner, window=window, pipe=pipe)
+
+
+def pipeline_alg_bytes(npix, nc, s, keep, B):
+    N = npix * npix
+    return {"K_A sim+col_ifft": nc * s * N * B, "K_B row_c2r+taper+r2c": nc * (2 + keep) * s * N * B,
+            "K_C col_fft+power+bin": (nc * s * N + N) * B}
+
+
+def run_headline(cx, args):
+    capi, mpi = cx.capi, cx.mpi
+    rank, ws = cx.rank, cx.ws
+    npix, B, W = args.npix, args.batch, max(args.warmup, 3)
+    pol = args.pol
+    dtype = np.float32 if args.dtype == "f32" else np.float64
+    P = build_pipeline(args, npix, pol, B, dtype, args.noise)
+    pipe, window, binner, th = P["pipe"], P["window"], P["binner"], P["th"]
+    mode = capi.NOISE_MODES[args.noise]
     # the real-space maps are materialised in HBM (SURVEY 8d anti-short-circuit rule) unless asked not to
     flags = pipe._flags(False, False, keep_maps=not args.no_keep_maps)
 
-    # shard: the job is ws*K*B realisations, contiguous blocks per rank (mpi.py:78-91)
-    total = ws * K * B
+    # shard: contiguous blocks of realisations per rank (mpi.py:78-91)
+    if args.scaling == "strong":
+        total = args.total
+        K = max(1, total // (ws * B))
+        total = K * B * ws
+    else:
+        K = args.steps
+        total = ws * K * B
     _, tasks = mpi.mpi_distribute(total, ws)
     my = np.array(tasks[rank], dtype=np.int64) + SEED0
-    seeds_pin = _capi.PinnedArray((K, B), np.int64)
+    seeds_pin = capi.PinnedArray((K, B), np.int64)
     seeds_pin.array[:] = my.reshape(K, B)
-    warm_pin = _capi.PinnedArray((B,), np.int64)
+    warm_pin = capi.PinnedArray((B,), np.int64)
     warm_pin.array[:] = np.arange(B) + 7
-    out_pin = _capi.PinnedArray((B, pipe.nspec, pipe.nbins), np.float64)
-
-    def barrier():
-        _capi.synchronize()
-        if ws > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    stat_tensors = None
-    if ws > 1:
-        n_p, s_p, c_p, d = pipe.stats_pointers()
-        stat_tensors = [torch.as_tensor(_DevView(n_p, (1,), "<i8"), device=f"cuda:{local}"),
-                        torch.as_tensor(_DevView(s_p, (d,), "<f8"), device=f"cuda:{local}"),
-                        torch.as_tensor(_DevView(c_p, (d, d), "<f8"), device=f"cuda:{local}")]
+    out_pin = capi.PinnedArray((B, pipe.nspec, pipe.nbins), np.float64)
 
     def reduce_stats():
-        if ws > 1:
-            for t in stat_tensors:     # N, SUM, CROSS (stats.py:1215-1217) over NCCL, in place
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        pipe.allreduce(cx.comm)          # ONE ncclAllReduce of [N | SUM | CROSS] (stats.py:1215-1217), no-op at 1 rank
 
     # ---- device-resident throughput
-    for _ in range(max(W, 3)):
+    for _ in range(W):
         pipe.run_raw(warm_pin.array, B, mode, flags, None)
     reduce_stats()
     pipe.reset_stats()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    timer = _capi.Timer()
-    l0 = _capi.launch_count()
-    timer.start()
-    for k in range(K):
-        pipe.run_raw(seeds_pin.array[k], B, mode, flags, None)
-    reduce_stats()
-    timer.stop()
-    ms = timer.elapsed_ms()
-    launches = _capi.launch_count() - l0
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    cx.barrier()
+    sampler = ClockSampler(cx.local)
+    sampler.start()
+    ms, launches = cx.timed(lambda k: pipe.run_raw(seeds_pin.array[k], B, mode, flags, None), K, reduce_stats)
+    clocks = sampler.stop()
     if ws > 1:
-        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        allc = [None] * ws
+        cx.dist.all_gather_object(allc, clocks)
+        if rank == 0:
+            sms = [c["sm_mhz"] for c in allc if c.get("sm_mhz")]
+            clocks = dict(allc[0])
+            clocks["per_rank_sm_mhz"] = [c.get("sm_mhz") for c in allc]
+            clocks["per_rank_samples"] = [c.get("samples") for c in allc]
+            clocks["reasons"] = sorted(set(r for c in allc for r in c.get("reasons", [])))
+            if sms:
+                clocks["sm_mhz"] = float(min(sms))
     N_stat, S, Cm = pipe.stats()
     value = total / (ms / 1e3)
+    # collective alone (device time of one more all-reduce of the packed triple)
+    ar_ms = None
+    if ws > 1:
+        ar_ms, _ = cx.timed(lambda k: reduce_stats(), 1)
+        pipe.reset_stats()
 
     # ---- end to end through the Python API with host buffers: pinned seeds in, bandpowers out, every step
     e2e = None
     if not args.no_e2e:
         pipe.reset_stats()
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(K):
-            pipe.run_raw(seeds_pin.array[k], B, mode, flags, _capi.ptr(out_pin.array))   # D2H + sync inside
-        _capi.synchronize()
-        dt = time.perf_counter() - t0
-        if ws > 1:
-            t = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = cx.wall(lambda k: pipe.run_raw(seeds_pin.array[k], B, mode, flags, capi.ptr(out_pin.array)), K, reduce_stats)
         e2e = {"value": total / dt, "unit": "maps/s", "h2d_bytes_per_step": int(B * 8),
                "d2h_bytes_per_step": int(out_pin.array.nbytes),
                "note": "SimPipeline.run_raw: seeds from pinned host memory -> bandpowers in pinned host memory each step; "
                        "the noise itself is drawn on the device (Philox), as the reference draws it in-process"}
 
-    # ---- the reference's per-call API with host arrays on both sides of every call (rank 0, a few maps):
-    # MapGen.get_map -> numpy map on the host -> x taper -> FourierCalc.power2d -> bin2D.bin
+    # ---- the reference's per-call API (rank 0, a few maps): MapGen.get_map -> x taper -> FourierCalc.power2d -> bin2D.bin
     percall = None
-    if rank == 0 and not args.no_e2e and not pol:
-        nmaps = 8
-        mg1 = maps.MapGen(shape, wcs, ps, noise=args.noise, dtype=dtype, max_batch=1)
-        fc1 = maps.FourierCalc(shape, wcs, dtype=dtype, max_batch=1)
-
-        def one(seed):
-            m = mg1.get_map(seed=int(seed))
-            if window is not None:
-                m = m * window
-            return binner.bin(fc1.power2d(m)[0])[1]
-        one(SEED0)
-        _capi.synchronize()
-        t0 = time.perf_counter()
-        for i in range(nmaps):
-            bp_last = one(SEED0 + i)
-        dt1 = time.perf_counter() - t0
-        mb = npix * npix * np.dtype(dtype).itemsize
-        percall = {"value": nmaps / dt1, "unit": "maps/s", "maps": nmaps,
-                   "h2d_bytes_per_map": int(2 * mb), "d2h_bytes_per_map": int(4 * mb),
-                   "note": "drop-in calls one map at a time with pageable numpy arrays, as the reference's signatures "
-                           "require: get_map returns the map (D2H), power2d takes it (H2D) and returns p2d and the "
-                           "complex k-map (D2H), bin2D.bin takes p2d (H2D); PCIe- and host-numpy-bound by construction, "
-                           "the batched SimPipeline call (e2e) is the product path"}
-        del mg1, fc1
+    if rank == 0 and not args.no_e2e and not args.no_extras and not pol:
+        percall = per_call_api(cx, args, P, dtype)
 
     if rank != 0:
-        if ws > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline: per-stage device times from CUDA events between the stages (rank 0)
     s = 4 if args.dtype == "f32" else 8
     Npx = npix * npix
     nc = 3 if pol else 1
     keep = 0 if args.no_keep_maps else 1
+    st_ms = profile_stages(capi, lambda: pipe.run_raw(seeds_pin.array[0], B, mode, flags, None), reps=5)
     if pipe.path == "fused":
-        # three hand-written kernels; bytes = what each one must move (half planes are s*N bytes)
-        names = {"sim_fill": "K_A sim+col_ifft", "cufft_inverse": "K_B row_c2r+taper+r2c", "power_bin": "K_C col_fft+power+bin",
-                 "statistics": "statistics"}
-        alg = {"K_A sim+col_ifft": nc * s * Npx, "K_B row_c2r+taper+r2c": nc * (2 + keep) * s * Npx,
-               "K_C col_fft+power+bin": nc * s * Npx + Npx, "statistics": 0}
-        ours_keys = ["K_A sim+col_ifft", "K_B row_c2r+taper+r2c", "K_C col_fft+power+bin"]
+        alg = pipeline_alg_bytes(npix, nc, s, keep, B)
+        note = ("per-kernel bytes are the fused kernel's own minimum traffic; see roofline_pipeline for the BASELINE metric's fraction "
+                "and roofline_true for the bytes the three kernels really move")
     else:
-        names = {k2: k2 for k2 in pipe.STAGES}
-        alg = {"sim_fill": nc * s * Npx, "cufft_inverse": nc * 4 * s * Npx, "window": nc * 2 * s * Npx if window is not None else 0,
-               "cufft_forward": nc * 4 * s * Npx, "power_bin": nc * s * Npx + Npx, "statistics": 0}
-        ours_keys = ["sim_fill", "window", "power_bin"]
-    reps = 5
-    acc = {k: 0.0 for k in alg}
-    for r in range(reps):
-        st = pipe.profile(seeds_pin.array[r % K], B, mode, flags)
-        for k2, v in st.items():
-            if k2 in names:
-                acc[names[k2]] += v / reps
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
-    stages = {}
-    for k2 in alg:
-        gbs = alg[k2] * B / (acc[k2] * 1e-3) / 1e9 if acc[k2] > 0 and alg[k2] else None
-        stages[k2] = {"ms_per_launch": acc[k2], "algorithmic_bytes_per_map": alg[k2], "achieved_gbs": gbs,
-                      "frac": gbs / peak if gbs else None}
-    ours = {k2: stages[k2] for k2 in ours_keys}
-    dom = max(ours, key=lambda k2: ours[k2]["ms_per_launch"])
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per map from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if npix == 2048 and args.dtype == "f64" and not pol and dom in tj["kernels"]:
-            traffic = tj["kernels"][dom]["dram_bytes_per_map"] * B
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dom] * B,
-                "note": "per-kernel bytes are the fused kernel's own minimum traffic; the kernels are bound by shared-memory "
-                        "bandwidth and FP64 issue (FFT butterflies, Box-Muller), not by HBM -- see roofline_pipeline for the "
-                        "BASELINE metric's fraction"}
-    pipe_bytes = (10 * s + 1) * Npx * nc if not pol else (30 * s + 1) * Npx
+        alg = {}
+        note = "cuFFT path"
+    key = f"{'IQU' if pol else 'T'}{npix}_{args.dtype}"
+    st_ms = {k: v for k, v in st_ms.items() if k in alg} if alg else st_ms
+    roofline = cx.roofline(st_ms, alg, key, note) if alg else None
+    pipe_bytes = (10 * s + 1) * Npx if not pol else (30 * s + 1) * Npx
     pipe_gbs = value / ws * pipe_bytes / 1e9
-    roofline_pipeline = {"bound": "hbm", "algorithmic_bytes_per_map": pipe_bytes, "achieved": pipe_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": pipe_gbs / peak,
-                         "note": "(10s+1)N per T map (SURVEY 8d); the taper RMW pass (2sN) is real traffic that the formula does not credit"}
+    roofline_pipeline = {"bound": "hbm", "algorithmic_bytes_per_map": pipe_bytes, "achieved": pipe_gbs, "peak": cx.peak,
+                         "unit": "GB/s", "frac": pipe_gbs / cx.peak,
+                         "note": "(10s+1)N per T map (SURVEY 8d: each 2-D FFT charged two passes); the taper RMW pass (2sN) is real traffic that the formula does not credit"}
+    true_bytes = sum(alg.values()) / B if alg else None
+    roofline_true = None
+    if true_bytes:
+        g2 = value / ws * true_bytes / 1e9
+        roofline_true = {"bytes_per_map_minimal_of_the_three_kernels": true_bytes, "achieved": g2, "frac": g2 / cx.peak,
+                         "unit": "GB/s", "note": "true HBM utilisation: the fused kernels' own minimal traffic x maps/s over the measured copy peak"}
 
     variants = None
     if ws == 1 and not args.no_extras:
         def timed(vmode, vflags, steps=4):
             pipe.run_raw(warm_pin.array, B, vmode, vflags, None)
-            _capi.synchronize()
-            tm = _capi.Timer()
-            tm.start()
-            for k in range(steps):
-                pipe.run_raw(seeds_pin.array[k % K], B, vmode, vflags, None)
-            tm.stop()
-            return steps * B / (tm.elapsed_ms() / 1e3)
+            ms2, _ = cx.timed(lambda k: pipe.run_raw(seeds_pin.array[k % K], B, vmode, vflags, None), steps)
+            return steps * B / (ms2 / 1e3)
         variants = {
-            "philox_fullplane_noise_maps_per_s": timed(_capi.NOISE_PHILOX, flags),
-            "philox_hermitian_noise_maps_per_s": timed(_capi.NOISE_PHILOX_HERMITIAN, flags),
-            "without_storing_maps_maps_per_s": timed(mode, flags & ~_capi.FLAG_KEEP_MAPS),
+            "philox_fullplane_noise_maps_per_s": timed(capi.NOISE_PHILOX, flags),
+            "philox_hermitian_noise_maps_per_s": timed(capi.NOISE_PHILOX_HERMITIAN, flags),
+            "without_storing_maps_maps_per_s": timed(mode, flags & ~capi.FLAG_KEEP_MAPS),
             "note": "same pipeline, 4 steps each: the reference's full complex-plane noise (4N normals/map) vs the "
                     "Hermitian half-plane draw (N normals/map); and without materialising the real-space maps in HBM"}
         pipe.reset_stats()
 
     cpu = None
     if ws == 1 and args.cpu_sample > 0:
-        cpu = cpu_baseline_sample(args, args.cpu_sample)
+        cpu = cpu_baseline_sample(npix, args.res, pol, not args.no_window, args.cpu_sample)
 
-    ratio = None
-    bp_mean = S[:pipe.nbins] / max(N_stat, 1)
     with np.errstate(all="ignore"):
+        bp_mean = S[:pipe.nbins] / max(N_stat, 1)
         w2 = float(np.mean(window ** 2)) if window is not None else 1.0
         ratio = float(np.nanmean(bp_mean / w2 / th.lCl("TT", binner.centers)))
 
     line = {
-        "metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": ws, "steps": K, "warmup": max(W, 3),
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": ws, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, B, ws),
         "clocks": clocks, "e2e": e2e, "e2e_per_call_api": percall, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_pipeline": roofline_pipeline, "stages": stages, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_pipeline": roofline_pipeline, "roofline_true": roofline_true,
+        "stages": cx.stages(st_ms, alg), "cpu_baseline": cpu,
+        "collective": {"what": "one ncclAllReduce(sum) of the packed float64 [N | SUM | CROSS] issued by liborphx.so (ox_pipeline_allreduce)",
+                       "bytes": int(8 * (1 + pipe.dim + pipe.dim ** 2)), "ms": ar_ms, "nccl_version": cx.comm.nccl_version()},
         "check": {"stat_N": int(N_stat), "mean_binned_over_theory_TT": ratio},
         "variants": variants, "pipeline_path": pipe.path,
-        "device": _capi.device_name(),
+        "device": capi.device_name(),
     }
-    print(json.dumps(line))
-    if ws > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def per_call_api(cx, args, P, dtype):
+    """The reference's call sequence, one map at a time, with its signatures: get_map -> *taper -> power2d -> bin."""
+    from orphics_b200 import maps
+    capi = cx.capi
+    shape, wcs, ps, window, binner = P["shape"], P["wcs"], P["ps"], P["window"], P["binner"]
+    nmaps = 16
+    mg1 = maps.MapGen(shape, wcs, ps, noise=args.noise, dtype=dtype, max_batch=1)
+    fc1 = maps.FourierCalc(shape, wcs, dtype=dtype, max_batch=1)
+
+    def one(seed):
+        m = mg1.get_map(seed=int(seed))
+        if window is not None:
+            m = m * window
+        return binner.bin(fc1.power2d(m)[0])[1]
+    one(SEED0)
+    capi.synchronize()
+    t0 = time.perf_counter()
+    for i in range(nmaps):
+        bp_last = np.asarray(one(SEED0 + i))
+    dt1 = time.perf_counter() - t0
+    info = getattr(maps, "PER_CALL_API_NOTE", None)
+    return {"value": nmaps / dt1, "unit": "maps/s", "maps": nmaps,
+            "note": info or "drop-in calls one map at a time: MapGen.get_map -> * taper -> FourierCalc.power2d -> bin2D.bin",
+            "checksum": float(np.nansum(bp_last))}
+
+
+# --------------------------------------------------------------------------- configs[2]: IQU
+def run_config_iqu(cx, args):
+    capi, mpi = cx.capi, cx.mpi
+    B, K, npix = 16, 16, 2048
+    P = build_pipeline(args, npix, True, B, np.float64, args.noise)
+    pipe = P["pipe"]
+    mode = capi.NOISE_MODES[args.noise]
+    flags = pipe._flags(False, False, keep_maps=True)
+    total = cx.ws * K * B
+    _, tasks = mpi.mpi_distribute(total, cx.ws)
+    seeds = capi.PinnedArray((K, B), np.int64)
+    seeds.array[:] = (np.array(tasks[cx.rank], dtype=np.int64) + SEED0).reshape(K, B)
+    out_pin = capi.PinnedArray((B, pipe.nspec, pipe.nbins), np.float64)
+    for _ in range(3):
+        pipe.run_raw(seeds.array[0], B, mode, flags, None)
+    pipe.reset_stats()
+    fin = lambda: pipe.allreduce(cx.comm)
+    ms, launches = cx.timed(lambda k: pipe.run_raw(seeds.array[k], B, mode, flags, None), K, fin)
+    pipe.reset_stats()
+    dt = cx.wall(lambda k: pipe.run_raw(seeds.array[k], B, mode, flags, capi.ptr(out_pin.array)), K, fin)
+    if cx.rank != 0:
+        return None
+    st_ms = profile_stages(capi, lambda: pipe.run_raw(seeds.array[0], B, mode, flags, None))
+    alg = pipeline_alg_bytes(npix, 3, 8, 1, B)
+    st_ms = {k: v for k, v in st_ms.items() if k in alg}
+    value = total / (ms / 1e3)
+    pb = (30 * 8 + 1) * npix * npix
+    cpu = None
+    if cx.ws == 1 and args.cpu_sample > 0:
+        cpu = cpu_baseline_sample(npix, args.res, True, not args.no_window, 3)
+        cpu["unit"] = "realisations/s"
+    return {"workload": "configs[2]: IQU 2048x2048 (0.5') sims with the TEB rotation, taper, 6 binned auto/cross spectra per realisation",
+            "value": value, "unit": "realisations/s", "ms_per_step": ms / K, "steps": K, "realisations_per_step_per_gpu": B,
+            "n_gpus": cx.ws, "scaling": "weak", "dtype": "f64", "gpu_launches": int(launches), "pipeline_path": pipe.path,
+            "e2e": {"value": total / dt, "unit": "realisations/s", "h2d_bytes_per_step": int(B * 8), "d2h_bytes_per_step": int(out_pin.array.nbytes)},
+            "roofline": cx.roofline(st_ms, alg, "IQU2048_f64"),
+            "roofline_pipeline": {"algorithmic_bytes_per_realisation": pb, "achieved": value / cx.ws * pb / 1e9, "unit": "GB/s",
+                                  "frac": value / cx.ws * pb / 1e9 / cx.peak, "note": "(30s+1)N per realisation (SURVEY 8d)"},
+            "stages": cx.stages(st_ms, alg), "cpu_baseline": cpu}
+
+
+# --------------------------------------------------------------------------- configs[3] / configs[4]: quadratic estimator
+def qe_alg_bytes(est, npix, s, nb):
+    """Minimal HBM bytes of each stage of the hand-written estimator chain for nb realisations (s = bytes per real,
+    half-plane complex array = s N bytes; the mean-field stack is complex128 whatever the arithmetic type)."""
+    N = npix * npix
+    nl = 3 if est == "TT" else 6
+    nin = 1 if est == "TT" else 2
+    return {"Q1 rows r2c": nin * 2 * s * N * nb, "Q2a cols fwd": nin * 2 * s * N * nb,
+            "Q2b legs cols inv": (nin + nl) * s * N * nb, "Q3a rows c2r": 2 * nl * s * N * nb,
+            "Q3b product rows r2c": (nl + 2) * s * N * nb, "Q4 cols fwd": 4 * s * N * nb,
+            "finish div+meanfield": (2 * s + 2 * s + 16) * N * nb}
+
+
+def run_config_qe(cx, args, est, npix, dtype_name, nb, total_real, label, scaling, cpu=True, shared=None):
+    from orphics_b200 import maps, lensing, cosmology, stats
+    capi, mpi = cx.capi, cx.mpi
+    rdt = np.float32 if dtype_name == "f32" else np.float64
+    s = 4 if dtype_name == "f32" else 8
+    t_setup = time.perf_counter()
+    shape, wcs = maps.rect_geometry(width_arcmin=npix * 0.5, px_res_arcmin=0.5)
+    th = cosmology.default_theory()
+    g = maps.Geometry.get(shape, wcs)
+    if shared and shared.get("npix") == npix:
+        qn, kw = shared["N"], shared["kw"]
+    else:
+        modl = g.modlmap()
+        beam = maps.gauss_beam(modl, 1.5)                                   # SURVEY 8d: beam 1.5', white noise 1 uK'
+        n2d = np.zeros(shape) + (1.0 * np.pi / 180 / 60) ** 2
+        tmask = maps.mask_kspace(shape, wcs, lmin=300, lmax=2000)
+        kmask = maps.mask_kspace(shape, wcs, lmin=20, lmax=3500)
+        kw = dict(noise2d=n2d, beam2d=beam, kmask=tmask, kmask_P=tmask, kmask_K=kmask, unlensed_equals_lensed=True)
+        qn = None
+        del modl
+    q = lensing.qest(shape, wcs, th, pol=(est == "EB"), dtype=rdt, max_batch=nb, quadnorm=qn, **kw)
+    if est not in q._plans:
+        q._make_plan(est)
+    setup_s = time.perf_counter() - t_setup
+    if shared is not None:
+        shared.update(npix=npix, N=q.N, kw=kw)
+    N = npix * npix
+    rng = np.random.RandomState(cx.rank)
+    # inputs resident in HBM: observed-like real maps (T, or E and B)
+    amp = 60.0 if est == "TT" else 3.0
+    xin = capi.PinnedArray((nb, npix, npix), rdt)
+    xin.array[:] = (rng.standard_normal((nb, npix, npix)) * amp).astype(rdt)
+    X = capi.DeviceBuffer(xin.array.nbytes).upload(xin.array)
+    yin = Y = None
+    if est == "EB":
+        yin = capi.PinnedArray((nb, npix, npix), rdt)
+        yin.array[:] = (rng.standard_normal((nb, npix, npix)) * 1.0).astype(rdt)
+        Y = capi.DeviceBuffer(yin.array.nbytes).upload(yin.array)
+    out = capi.DeviceBuffer(nb * N * 2 * s)
+    h = q._plans[est][0]
+    import ctypes as C
+
+    def step(k=0):
+        capi.check(capi.lib.ox_qe_reconstruct(h, C.c_void_p(X.ptr), C.c_void_p(Y.ptr) if Y else None, capi.OX_DEVICE, nb, 0, 1, 1,
+                                              C.c_void_p(out.ptr), capi.OX_DEVICE))
+    if scaling == "strong":
+        mine = len(mpi.mpi_distribute(total_real, cx.ws)[1][cx.rank])
+    else:
+        mine = total_real
+    K = max(1, mine // nb)
+    done = K * nb * cx.ws
+    for _ in range(3):
+        step()
+    q.reset_meanfield(est)
+    fin = lambda: q.allreduce_meanfield(est, cx.comm)       # ONE ncclAllReduce of [stack | count] (stats.py:1227-1228)
+    ms, launches = cx.timed(step, K, fin)
+    count = q.meanfield_count(est) if cx.rank == 0 else None
+    ar_ms = None
+    if cx.ws > 1:
+        ar_ms, _ = cx.timed(lambda k: fin(), 1)
+    # end to end through the public API with host buffers: pinned maps in -> kappa maps in pinned memory out
+    kout = capi.PinnedArray((nb, npix, npix), rdt)
+    Ke = min(K, 2)
+    q.kappa_from_maps(est, xin.array, None if yin is None else yin.array, out=kout.array)
+    dt = cx.wall(lambda k: q.kappa_from_maps(est, xin.array, None if yin is None else yin.array, accumulate_meanfield=True,
+                                             out=kout.array), Ke)
+    e2e_val = Ke * nb * cx.ws / dt
+    if cx.rank != 0:
+        return None
+    st_ms = profile_stages(capi, step)
+    alg = qe_alg_bytes(est, npix, s, nb)
+    st_ms = {k: v for k, v in st_ms.items() if k in alg}
+    value = done / (ms / 1e3)
+    pb = (38 if est == "TT" else 76) * s * N
+    res = {"workload": label, "value": value, "unit": "realisations/s", "ms_per_step": ms / K, "steps": K,
+           "realisations_per_step_per_gpu": nb, "realisations": done, "n_gpus": cx.ws, "scaling": scaling, "dtype": dtype_name,
+           "gpu_launches": int(launches), "path": q.path(est), "setup_seconds": setup_s,
+           "meanfield_count_after_allreduce": count,
+           "collective": {"what": "one ncclAllReduce(sum) of the packed float64 [mean-field stack | count] (ox_qe_meanfield_allreduce)",
+                          "bytes": int(8 * (2 * (npix * (npix // 2 + 1)) + 1)), "ms": ar_ms},
+           "e2e": {"value": e2e_val, "unit": "realisations/s", "h2d_bytes_per_step": int(xin.array.nbytes * (2 if yin is not None else 1)),
+                   "d2h_bytes_per_step": int(kout.array.nbytes),
+                   "note": "qest.kappa_from_maps: observed maps from pinned host memory -> kappa maps in pinned host memory "
+                           "(+ mean-field accumulate on the device); PCIe-bound"},
+           "roofline": cx.roofline(st_ms, alg, f"QE_{est}{npix}_{dtype_name}"),
+           "roofline_pipeline": {"algorithmic_bytes_per_realisation": pb, "achieved": value / cx.ws * pb / 1e9, "unit": "GB/s",
+                                 "frac": value / cx.ws * pb / 1e9 / cx.peak,
+                                 "note": ("38 s N" if est == "TT" else "76 s N") + " per realisation (SURVEY 8d: cuFFT-chain accounting, each 2-D FFT two passes)"},
+           "stages": cx.stages(st_ms, alg), "cpu_baseline": None}
+    if cpu and cx.ws == 1 and args.cpu_sample > 0:
+        res["cpu_baseline"] = qe_cpu_baseline(q, est, npix, xin.array[0], None if yin is None else yin.array[0])
+    for b in (X, Y, out):
+        if b is not None:
+            b.free()
+    return res
+
+
+def qe_cpu_baseline(q, est, npix, x, y):
+    """One realisation of the numpy oracle's kappa_from_map chain (filters handed in, set-up excluded) with the
+    FFTs on all host cores."""
+    import scipy.fft
+    from oracle import qe_np, maps_np as omaps
+    so, wo = omaps.rect_geometry(width_arcmin=npix * 0.5, px_res_arcmin=0.5)
+    Nn = q.N
+    tables = {"WXY_" + est: Nn.WXY(est), "WY_" + est[1] * 2: Nn.WY(est[1] * 2)}
+    qo = qe_np.qest_from_tables(so, wo, tables, {est: np.asarray(Nn.AL[est])}, Nn.fmaskK)
+    cores = host_cores()
+    x64 = np.asarray(x, dtype=np.float64)
+    y64 = None if y is None else np.asarray(y, dtype=np.float64)
+    with scipy.fft.set_workers(cores):
+        t0 = time.perf_counter()
+        if est == "TT":
+            qo.kappa_from_map("TT", x64, returnFt=True)
+        else:
+            qo.kappa_from_map("EB", None, x64, y64, returnFt=True)
+        dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "realisations/s", "cores": cores, "kind": "port",
+            "sample": f"1 realisation of the {est} estimator at {npix}^2 through the numpy oracle (qe_np.kappa_from_map, returnFt), "
+                      f"scipy.fft on {cores} threads, numpy elementwise passes on 1; filters and A_L handed in (set-up excluded)"}
+
+
+def run_ours(args):
+    cx = Ctx()
+    line = run_headline(cx, args)
+    want = [] if args.configs == "none" else (["2", "3", "4"] if args.configs == "all" else args.configs.split(","))
+    configs = {}
+    t0 = time.perf_counter()
+    if "2" in want and not args.pol:
+        r = run_config_iqu(cx, args)
+        if r:
+            configs["configs[2]"] = r
+    if "3" in want:
+        r = run_config_qe(cx, args, "TT", 4096, "f64", 8, 512, "configs[3]: TT Hu-Okamoto quadratic estimator on 4096x4096 (0.5') observed maps "
+                          "(beam 1.5', noise 1 uK', l in (300,2000)), 512 realisations sharded over the GPUs, kappa_hat(l) + mean-field "
+                          "accumulate, one mean-field all-reduce", "strong")
+        if r:
+            configs["configs[3]"] = r
+    if "4" in want:
+        shared = {}
+        for dt_name in ("f64", "f32"):
+            r = run_config_qe(cx, args, "EB", 8192, dt_name, 2, 16, f"configs[4]: EB quadratic estimator at 8192x8192 (0.5') {dt_name}, "
+                              "16 realisations per GPU from real E/B maps, kappa_hat(l) + mean-field accumulate, one mean-field all-reduce",
+                              "weak", cpu=(dt_name == "f64"), shared=shared)
+            if r:
+                if dt_name == "f32" and "configs[4] fp64" in configs:
+                    base = configs["configs[4] fp64"]["cpu_baseline"]
+                    r["cpu_baseline"] = dict(base, note="the reference has no float32 path: fp64 CPU figure") if base else None
+                configs[f"configs[4] fp{dt_name[1:]}"] = r
+    if cx.rank == 0:
+        line["configs"] = configs
+        line["configs_seconds"] = time.perf_counter() - t0
+        print(json.dumps(line))
+    cx.comm.free()
+    if cx.ws > 1:
+        cx.dist.destroy_process_group()
 
 
 def main():

@@ -208,8 +208,7 @@ int ox_qe_meanfield_reset(ox_qeplan *q);
 /* which implementation the plan runs for Hermitian inputs: 0 = full-plane c2c chain on cuFFT (unsymmetric
  * filters, or EB on maps that are not powers of two), 1 = TT on half planes with cuFFT r2c/c2r, 2 = TT and
  * 3 = EB on half planes with the hand-written FFT passes (power-of-two maps; ORPHX_QE=cufft in the
- * environment disables 2 and 3).  already_ft inputs that are not Hermitian (checked on a sample of the
- * pixels) always take the c2c chain. */
+ * environment disables 2 and 3).  already_ft inputs that are not Hermitian (checked on every pixel pair) always take the c2c chain. */
 int ox_qe_path(ox_qeplan *q);
 
 /* maps.filter_map (maps.py:1922-1923): Re(ifft(fft(m) * kfilter)) / Npix for nbatch x ncomp real maps;

@@ -159,3 +159,31 @@ class qest:
         return enmap.ndmap(_ifft(kappaft).real, self.wcs)
 
     reconstruct = kappa_from_map
+
+
+class _TableNorm:
+    """QuadNorm stand-in holding ready-made filter tables (bench.py's cpu_baseline: the per-realisation chain is
+    what is timed, so the set-up arithmetic above is skipped and the filters are handed in)."""
+
+    def __init__(self, shape, wcs, tables, AL, kmask_K, method="cylindrical"):
+        ly, lx = enmap.laxes(shape, wcs, method)
+        self.lyMap, self.lxMap = np.meshgrid(ly, lx, indexing="ij")
+        self.thetaMap = np.arctan2(self.lyMap, self.lxMap)
+        self._t, self.AL, self.fmaskK = dict(tables), dict(AL), kmask_K
+
+    def WXY(self, XY):
+        return self._t["WXY_" + XY]
+
+    def WY(self, YY):
+        return self._t["WY_" + YY]
+
+
+def qest_from_tables(shape, wcs, tables, AL, kmask_K=None, method="cylindrical"):
+    """qest whose kappa_from_map runs the chain above on given tables: tables = {"WXY_TT": .., "WY_TT": ..,
+    "WXY_EB": .., "WY_BB": ..} (full-plane float64), AL = {"TT": .., "EB": ..}."""
+    q = qest.__new__(qest)
+    q.shape, q.wcs = shape, wcs
+    q.N = _TableNorm(shape, wcs, tables, AL, kmask_K, method)
+    q.pol = "EB" in AL
+    q.phaseY = np.cos(2. * q.N.thetaMap) + 1.j * np.sin(2. * q.N.thetaMap)
+    return q

@@ -333,20 +333,23 @@ __global__ void eb_leg_tables_kernel(const T *__restrict__ wxyT, const T *__rest
   }
 }
 
-// sum over a sample of pixels (every 16th row) of |k(p) - conj k(p')|^2 and |k(p)|^2: acc[0], acc[1]
+// EXHAUSTIVE Hermitian test: sum over every pair {p, p'} (rows 0..ny/2 against their mirror rows, so each element
+// of the plane is read once: 2 s N bytes against the >= 28 s N of the chain) of |k(p) - conj k(p')|^2 and
+// |k(p)|^2 + |k(p')|^2: acc[0], acc[1].  The caller takes the half-plane path only when the anti-Hermitian part
+// carries less than 1e-20 (fp64) of the power, i.e. when dropping it changes the result by < 1e-10 in norm.
 template <typename T2>
 __global__ void herm_check_kernel(const T2 *__restrict__ k, int ny, int nx, double *__restrict__ acc) {
   const long long plane = blockIdx.y;
   const T2 *kp = k + plane * (long long)ny * nx;
   double d2 = 0.0, n2 = 0.0;
-  const int nrows = (ny + 15) / 16;
+  const int nrows = ny / 2 + 1;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)nrows * nx; t += (long long)gridDim.x * blockDim.x) {
-    const int iy = (int)(t / nx) * 16, ix = (int)(t % nx);
+    const int iy = (int)(t / nx), ix = (int)(t % nx);
     const int my = iy ? ny - iy : 0, mx = ix ? nx - ix : 0;
     const T2 a = kp[(long long)iy * nx + ix], b = kp[(long long)my * nx + mx];
     const double dx = (double)a.x - (double)b.x, dy = (double)a.y + (double)b.y;
     d2 += dx * dx + dy * dy;
-    n2 += (double)a.x * a.x + (double)a.y * a.y;
+    n2 += (double)a.x * a.x + (double)a.y * a.y + (double)b.x * b.x + (double)b.y * b.y;
   }
   for (int o = 16; o > 0; o >>= 1) {
     d2 += __shfl_xor_sync(0xffffffffu, d2, o);
@@ -628,8 +631,8 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
   const double invn = 1.0 / ((double)ny * (double)nx);
   const double *ly = g->ly.as<double>(), *lx = g->lx.as<double>();
   const bool two = (y != nullptr && y != x);
-  // the half-plane paths need Hermitian Fourier inputs (transforms of real maps): verified on a sample of
-  // the pixels when the caller hands in k-maps; anything else goes through the reference's c2c chain
+  // the half-plane paths need Hermitian Fourier inputs (transforms of real maps): verified on EVERY pixel pair
+  // when the caller hands in k-maps; anything else goes through the reference's c2c chain
   bool real = q->real_path && (q->est == OX_QE_TT || q->fused);
   if (real && already_ft) {
     OX_TRY(q->herm.ensure(2 * sizeof(double)));
@@ -637,7 +640,7 @@ int reconstruct_T(ox_qeplan *q, const void *x, const void *y, int where, int nb,
     const void *staged[2] = {nullptr, nullptr};
     for (int leg = 0; leg < (two ? 2 : 1); leg++) {
       OX_TRY(stage_in(leg ? y : x, where, sizeof(T2) * (size_t)nb * n, leg ? q->full2 : q->full, &staged[leg]));
-      herm_check_kernel<T2><<<dim3(sm_count(), nb), QT, 0, g_stream>>>((const T2 *)staged[leg], ny, nx, q->herm.as<double>());
+      herm_check_kernel<T2><<<dim3(sm_count() * 4, nb), QT, 0, g_stream>>>((const T2 *)staged[leg], ny, nx, q->herm.as<double>());
       OX_KERNEL_CHECK();
     }
     // host inputs are on the device now: hand the staged copies on instead of uploading them again

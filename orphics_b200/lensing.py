@@ -17,6 +17,10 @@ from ._capi import lib, check, ptr, OX_HOST
 from . import enmap as _enmap
 from .enmap import Geometry, ndmap
 
+#: bound on max|kappa - kappa_ref| / max|kappa_ref| of the float32 estimator against the float64 reference chain
+#: on the same (float32-representable) inputs; see include/orphx.h (ox_qeplan_create) and DESIGN.md
+QE_FP32_BOUND = 2e-4
+
 
 def _fmask(arr, mask):
     arr = arr.copy()
@@ -128,7 +132,7 @@ def _symmetric(a, rtol=0.):
 class qest(object):
     def __init__(self, shape, wcs, theory, noise2d=None, beam2d=None, kmask=None, noise2d_P=None, kmask_P=None,
                  kmask_K=None, pol=False, grad_cut=None, unlensed_equals_lensed=False, bigell=9000, noise2d_B=None,
-                 noise_keys2d=None, dtype=np.float64, max_batch=1, method=None):
+                 noise_keys2d=None, dtype=np.float64, max_batch=1, method=None, quadnorm=None):
         _capi.require_device()
         self.shape, self.wcs = tuple(int(s) for s in shape), wcs
         self.geometry = Geometry.get(shape, wcs, method)
@@ -137,15 +141,18 @@ class qest(object):
         self.pol = pol
         self._fftplan = C.c_void_p()   # float64 single-component plan for the set-up transforms
         check(lib.ox_powerplan_create(self.geometry.handle, 1, _capi.OX_F64, 4, C.byref(self._fftplan)))
-        self.N = QuadNorm(shape, wcs, theory, noise2d, noise2d_P, noise2d_B, beam2d, kmask, kmask_P, kmask_K, grad_cut,
-                          unlensed_equals_lensed, bigell, self.geometry, self._fftplan)
+        # quadnorm: filters and A_L of another qest on the same geometry (e.g. the float64 estimator's, reused
+        # by a float32 one) instead of building them again
+        self.N = quadnorm if quadnorm is not None else QuadNorm(
+            shape, wcs, theory, noise2d, noise2d_P, noise2d_B, beam2d, kmask, kmask_P, kmask_K, grad_cut,
+            unlensed_equals_lensed, bigell, self.geometry, self._fftplan)
         self._plans = {}
         for XY in (('TT', 'EB') if pol else ('TT',)):
             self._make_plan(XY)
 
     def _make_plan(self, XY):
         N = self.N
-        AL = N.getNlkk2d(XY)
+        AL = N.AL[XY] if XY in N.AL else N.getNlkk2d(XY)
         wxy = np.ascontiguousarray(N.WXY(XY), dtype=np.float64)
         wy = np.ascontiguousarray(N.WY(XY[1] + XY[1]), dtype=np.float64)
         norm = np.ascontiguousarray(_fmask(np.nan_to_num(AL), N.fmaskK), dtype=np.float64)
@@ -169,7 +176,7 @@ class qest(object):
             self._make_plan(XY)
         return {0: 'c2c', 1: 'half', 2: 'fused', 3: 'fused_eb'}[lib.ox_qe_path(self._plans[XY][0])]
 
-    def _run(self, XY, X, Y, alreadyFTed, returnFt, accumulate):
+    def _run(self, XY, X, Y, alreadyFTed, returnFt, accumulate, out=None):
         if XY not in self._plans:
             if XY in ('TT', 'EB'):
                 self._make_plan(XY)
@@ -184,7 +191,11 @@ class qest(object):
         nb = x.shape[0]
         if nb > self.max_batch:
             raise ValueError(f"{nb} realisations but max_batch={self.max_batch}")
-        out = np.empty((nb,) + g, dtype=cdt if returnFt else rdt)
+        odt = cdt if returnFt else rdt
+        if out is None:
+            out = np.empty((nb,) + g, dtype=odt)
+        elif out.dtype != odt or out.size != nb * g[0] * g[1] or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous array of the result's dtype and size")
         check(lib.ox_qe_reconstruct(h, ptr(x), ptr(y), OX_HOST, nb, int(bool(alreadyFTed)), int(bool(returnFt)),
                                     int(bool(accumulate)), ptr(out), OX_HOST))
         return out
@@ -204,9 +215,10 @@ class qest(object):
 
     reconstruct = kappa_from_map
 
-    def kappa_from_maps(self, XY, X, Y=None, alreadyFTed=False, returnFt=False, accumulate_meanfield=False):
-        """Batched: X (and Y) are stacks (nbatch, Ny, Nx); returns (nbatch, Ny, Nx)."""
-        return self._run(XY, X, Y, alreadyFTed, returnFt, accumulate_meanfield)
+    def kappa_from_maps(self, XY, X, Y=None, alreadyFTed=False, returnFt=False, accumulate_meanfield=False, out=None):
+        """Batched: X (and Y) are stacks (nbatch, Ny, Nx); returns (nbatch, Ny, Nx).  out: optional result array
+        (e.g. pinned host memory, _capi.PinnedArray) to fill instead of a fresh pageable one."""
+        return self._run(XY, X, Y, alreadyFTed, returnFt, accumulate_meanfield, out=out)
 
     def meanfield(self, XY):
         """(sum of kappa_hat(l) on the half plane, count) accumulated on the device."""
@@ -216,6 +228,13 @@ class qest(object):
         check(lib.ox_memcpy_d2h(ptr(packed), C.c_void_p(p), packed.nbytes))
         acc = packed[:2 * nel].view(np.complex128).reshape(ny, nx // 2 + 1).copy()
         return acc, int(round(packed[2 * nel]))
+
+    def meanfield_count(self, XY):
+        """Number of realisations in the device mean-field stack (8-byte read)."""
+        p, nel = self.meanfield_pointer(XY)
+        c = np.empty(1, dtype=np.float64)
+        check(lib.ox_memcpy_d2h(ptr(c), C.c_void_p(p + 16 * nel), 8))
+        return int(round(c[0]))
 
     def meanfield_pointer(self, XY):
         """Device address of the packed float64 [stack (complex128 half plane) | count] and the stack's

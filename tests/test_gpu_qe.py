@@ -229,3 +229,23 @@ def test_flat_lensing_sims_match_oracle(pol, theory):
     assert relerr(lens, olens) < TOL64                          # identical inputs: the transform chain itself
     skipped = sims.get_sim(seed_cmb=1, seed_noise=3, skip_lensing=True, cfrac=0.5)
     assert skipped.shape[-2:] == (64, 64)
+
+
+def test_hermitian_check_is_exhaustive(theory):
+    """A k-map that is Hermitian everywhere except in ONE pixel pair (on a row that a sampled check would skip) must
+    not take the half-plane path: the result has to be the reference's full-plane chain on that input."""
+    shape, wcs, so, wo, q, qo = setup(512, 2.0, theory, True)
+    assert q.path("TT") == "fused"
+    qo.N.AL["TT"] = np.asarray(q.N.AL["TT"])
+    rng = np.random.RandomState(9)
+    kT = np.fft.fft2(rng.standard_normal(shape) * 50)
+    iy, ix = 37, 11                                   # 37 is not a multiple of 16; |l| ~ 800 is inside the TT filter
+    assert 300 < np.hypot(q.geometry.ly[iy], q.geometry.lx[ix]) < 2000
+    kT[iy, ix] *= 3.0                                 # breaks k(p') = conj k(p) for this pair only
+    got = q.kappa_from_map("TT", kT, alreadyFTed=True, returnFt=True)
+    want = qo.kappa_from_map("TT", kT, alreadyFTed=True, returnFt=True)
+    assert relerr(got, want) < TOL64
+    # and the symmetric input still takes the fast path with the same answer
+    kS = np.fft.fft2(np.fft.ifft2(kT).real)
+    assert relerr(q.kappa_from_map("TT", kS, alreadyFTed=True, returnFt=True),
+                  qo.kappa_from_map("TT", kS, alreadyFTed=True, returnFt=True)) < TOL64

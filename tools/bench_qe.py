@@ -2,8 +2,8 @@
 with inputs resident in HBM, and the fraction of the SURVEY 8d roofline (TT: 38 s N bytes per
 realisation incl. the mean-field accumulate; EB ~ 76 s N).  Usage: python tools/bench_qe.py [npix] [batch] [f64|f32] [TT|EB] [nreal]
 Under torchrun (WORLD_SIZE > 1) the nreal realisations (default 10 steps x batch per rank) are split over the
-ranks with the reference's rule (mpi.py:78-91) and the mean-field stack + count are summed with one NCCL
-all-reduce each inside the timed region (BASELINE configs[3]: 512 realisations plus mean-field allreduce)."""
+ranks with the reference's rule (mpi.py:78-91) and the packed mean-field stack + count are summed with one NCCL
+all-reduce (ox_qe_meanfield_allreduce) inside the timed region (BASELINE configs[3]: 512 realisations plus mean-field allreduce)."""
 import ctypes as C
 import json
 import os
@@ -56,27 +56,16 @@ def step():
                                 C.c_void_p(out.ptr), _capi.OX_DEVICE))
 
 
-class _DevView:
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
-
-
 nreal = int(sys.argv[5]) if len(sys.argv) > 5 else 10 * nb * ws
 mine = len(mpi.mpi_distribute(nreal, ws)[1][rank])
 K = max(1, mine // nb)
-mf_tensors = None
+comm = mpi.NcclComm(rank, ws)     # data plane: one ncclAllReduce of the packed [stack | count] issued by liborphx.so
 if ws > 1:
     import torch
     import torch.distributed as dist
-    acc, cnt, nel = C.c_void_p(), C.c_void_p(), C.c_longlong()
-    check(lib.ox_qe_meanfield(h, C.byref(acc), C.byref(cnt), C.byref(nel)))
-    mf_tensors = [torch.as_tensor(_DevView(acc.value, (2 * nel.value,), "<f8"), device=f"cuda:{local}"),
-                  torch.as_tensor(_DevView(cnt.value, (1,), "<i8"), device=f"cuda:{local}")]
 for _ in range(3):
     step()
-if ws > 1:
-    for t_ in mf_tensors:
-        dist.all_reduce(t_)
+q.allreduce_meanfield(est, comm)
 check(lib.ox_qe_meanfield_reset(h))
 _capi.synchronize()
 if ws > 1:
@@ -91,20 +80,17 @@ t.stop()
 ms = t.elapsed_ms()
 ar_ms = 0.0
 if ws > 1:
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for t_ in mf_tensors:                 # Statistics.add_stack / allreduce (stats.py:1227-1228) over NCCL, in place
-        dist.all_reduce(t_)
-    e1.record()
-    torch.cuda.synchronize()
-    ar_ms = e0.elapsed_time(e1)
+    t2 = _capi.Timer()
+    t2.start()
+    q.allreduce_meanfield(est, comm)     # Statistics.add_stack / allreduce (stats.py:1227-1228)
+    t2.stop()
+    ar_ms = t2.elapsed_ms()
     tt = torch.tensor([ms + ar_ms], device=f"cuda:{local}", dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = float(tt.item())
-    count = int(mf_tensors[1].item())
 else:
     total_ms = ms
-    count = K * nb
+count = q.meanfield_count(est)
 rate = ws * K * nb / (total_ms / 1e3)
 bytes_per = (38 if est == "TT" else 76) * s * N
 peak = 6550.1
