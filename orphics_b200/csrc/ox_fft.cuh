@@ -278,7 +278,7 @@ struct BlockFFT {
   template <int DIR, int R, int Ns, int WOFF, bool FIRST, bool LAST, bool SYNC_BEFORE_WRITE, bool SYNC_AFTER_WRITE,
             class LoadOp, class StoreOp>
   static __device__ __forceinline__ void stage(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
-                                               const StoreOp &st) {
+                                               const StoreOp &st, int bar_bw = -1, int cnt_bw = 0) {
     constexpr int Q = 16 / R;
     constexpr bool PF = LAST && Q > 1 && has_prefetch<StoreOp>::value;
     T2 v[16];
@@ -299,7 +299,12 @@ struct BlockFFT {
       if (R == 4) dft4<DIR>(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       if (R == 2) dft2<DIR>(v[q * 2], v[q * 2 + 1]);
     }
-    if (SYNC_BEFORE_WRITE) fft_sync(bar, NT);
+    if (SYNC_BEFORE_WRITE) {
+      // (bar_bw >= 0: the first stage read a buffer shared with OTHER transforms -- e.g. a TMA tile holding
+      // several rows interleaved -- so its reads are fenced by the wider barrier of cnt_bw threads)
+      if (bar_bw >= 0) fft_sync(bar_bw, cnt_bw);
+      else fft_sync(bar, NT);
+    }
 #pragma unroll
     for (int q = 0; q < Q; q++) {
       const int j = u + q * NT;
@@ -324,7 +329,7 @@ struct BlockFFT {
 
   template <int DIR, int I, int Ns, bool IN_SMEM, bool OUT_SMEM, class LoadOp, class StoreOp>
   static __device__ __forceinline__ void from(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
-                                              const StoreOp &st) {
+                                              const StoreOp &st, int bar0 = -1, int cnt0 = 0) {
     constexpr int rem = L / Ns;
     constexpr bool first = (I == 0);
     // the reads of a stage must complete before its writes unless the reads did not touch smem
@@ -333,17 +338,20 @@ struct BlockFFT {
       constexpr bool last = (rem == 16);
       constexpr bool sync_aw = last ? OUT_SMEM : true;
       // when the last stage does not write smem nobody waits for its reads either
-      stage<DIR, 16, Ns, (I > 0 ? I - 1 : 0), first, last, (last && !OUT_SMEM) ? false : sync_bw, sync_aw>(s, tws, u, bar, ld, st);
+      stage<DIR, 16, Ns, (I > 0 ? I - 1 : 0), first, last, (last && !OUT_SMEM) ? false : sync_bw, sync_aw>(s, tws, u, bar, ld, st,
+                                                                                                          first ? bar0 : -1, cnt0);
       if constexpr (!last) from<DIR, I + 1, Ns * 16, IN_SMEM, OUT_SMEM>(s, tws, u, bar, ld, st);
     } else if constexpr (rem > 1) {
-      stage<DIR, rem, Ns, (P::N16 > 1 ? P::N16 - 1 : 0), first, true, OUT_SMEM ? sync_bw : false, OUT_SMEM>(s, tws, u, bar, ld, st);
+      stage<DIR, rem, Ns, (P::N16 > 1 ? P::N16 - 1 : 0), first, true, OUT_SMEM ? sync_bw : false, OUT_SMEM>(s, tws, u, bar, ld, st,
+                                                                                                            first ? bar0 : -1, cnt0);
     }
   }
 
   template <int DIR, bool IN_SMEM, bool OUT_SMEM, class LoadOp, class StoreOp>
+  // bar0 / cnt0: optional wider named barrier (id, thread count) fencing the FIRST stage's reads from its writes
   static __device__ __forceinline__ void run(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
-                                             const StoreOp &st) {
-    from<DIR, 0, 1, IN_SMEM, OUT_SMEM>(s, tws, u, bar, ld, st);
+                                             const StoreOp &st, int bar0 = -1, int cnt0 = 0) {
+    from<DIR, 0, 1, IN_SMEM, OUT_SMEM>(s, tws, u, bar, ld, st, bar0, cnt0);
   }
 
   // plain in-place transform of s (input already in s and synchronised; output in s, synchronised)

@@ -339,10 +339,20 @@ struct RowCfg {
   static constexpr int R = FIT >= WANT ? WANT : (FIT >= MINR ? (FIT >= 4 ? 4 : (FIT >= 2 ? 2 : 1)) : MINR);
 };
 
+}  // namespace oxk
+#include "ox_row_tma.cuh"
+namespace oxk {
+
 template <typename T, int MX, int MODE>
 int launch_row_mode(RowArgs<T> &a, long long nplanes) {
   typedef typename V2<T>::type T2;
   constexpr int R = RowCfg<T, MX>::R;
+  {
+    // Blackwell path: persistent CTAs fed by the TMA unit (ox_row_tma.cuh); ORPHX_KB=legacy keeps the kernel below
+    bool launched = false;
+    OX_TRY((launch_row_tma<T, MX, MODE>(a, nplanes, &launched)));
+    if (launched) return OX_OK;
+  }
   size_t smem = sizeof(T2) * R * padded_size(MX);
   OX_REQUIRE(smem <= SMEM_MAX, "fused row: %d rows of %d need %zu B of shared memory", R, MX, smem);
   OX_REQUIRE(a.ny % R == 0, "ny must be a multiple of %d", R);

@@ -18,8 +18,9 @@ from . import enmap as _enmap
 from .enmap import Geometry, ndmap
 
 #: bound on max|kappa - kappa_ref| / max|kappa_ref| of the float32 estimator against the float64 reference chain
-#: on the same (float32-representable) inputs; see include/orphx.h (ox_qeplan_create) and DESIGN.md
-QE_FP32_BOUND = 2e-4
+#: on the same (float32-representable) inputs: north_star's 1e-5.  Measured on B200: 7e-7 (TT) / 8e-7 (EB) at 512^2
+#: on both the hand-written and the cuFFT chains (tools/diag_fp32_qe.py, profiles/r02_fp32_qe.txt)
+QE_FP32_BOUND = 1e-5
 
 
 def _fmask(arr, mask):

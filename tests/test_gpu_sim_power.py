@@ -396,3 +396,45 @@ def test_multi_pow_on_device_matches_eigpow(theory):
     mg = maps.MapGen(shape, wcs, cov4, pixel_units=True)
     assert relerr(mg.covsqrt, cs3) < 1e-9
     assert relerr(mg.get_map(seed=3), og.get_map(seed=3)) < 1e-9
+
+
+@pytest.mark.parametrize("pol", [False, True])
+def test_tma_row_pass_is_bit_identical_to_the_legacy_row_pass(pol, theory, monkeypatch):
+    """The persistent TMA row kernel (ox_row_tma.cuh: cp.async.bulk.tensor tiles, three slots, two groups per CTA)
+    runs the same butterflies in the same order as the one-tile-per-CTA kernel: bandpowers and stored maps must be
+    bit-identical, on a 512 x 2048 patch (nx/2 = 1024: the 2048^2 configuration's row length) -- and match the
+    oracle on numpy seeds."""
+    from orphics_b200 import maps, stats
+    ny, nx, res = 512, 2048, 1.0
+    shape, wcs = maps.rect_geometry(width_arcmin=nx * res, px_res_arcmin=res, height_arcmin=ny * res, pol=pol)
+    so, wo = omaps.rect_geometry(width_arcmin=nx * res, px_res_arcmin=res, height_arcmin=ny * res, pol=pol)
+    assert tuple(shape[-2:]) == (ny, nx)
+    modl = np.asarray(oenmap.modlmap(so, wo))
+    ps = otheory.power_from_theory(np.arange(0, modl.max() + 1, 1.0), theory, lensed=True, pol=pol)
+    og, ofc, ob = omaps.MapGen(so, wo, ps), omaps.FourierCalc(so, wo), ostats.bin2D(modl, EDGES)
+    taper = np.asarray(maps.get_taper(shape, wcs)[0])
+    nsim = 5                                                     # 5 planes x 128 row tiles: odd tile counts per CTA
+    out = {}
+    for kb in ("legacy", "tma"):
+        monkeypatch.setenv("ORPHX_KB", kb)
+        mg = maps.MapGen(shape, wcs, ps, noise="numpy", max_batch=nsim)
+        fc = maps.FourierCalc(shape, wcs, max_batch=nsim)
+        b = stats.bin2D(fc.geometry.modlmap(), EDGES, geometry=fc.geometry)
+        pipe = maps.SimPipeline(mg, fc, b, window=taper)
+        assert pipe.path == "fused"
+        bp = pipe.run(range(40, 40 + nsim), keep_maps=True)
+        out[kb] = (bp, pipe.last_maps(nsim))
+    assert np.array_equal(out["tma"][0], out["legacy"][0], equal_nan=True)
+    assert np.array_equal(out["tma"][1], out["legacy"][1])
+    bp, stored = out["tma"]
+    pairs = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)] if pol else [(0, 0)]
+    auto = {0: 0, 1: 3, 2: 5}
+    for i in (0, nsim - 1):
+        mo = og.get_map(seed=40 + i)
+        assert relerr(stored[i] if pol else stored[i, 0], mo) < TOL64
+        p2o = ofc.power2d(oenmap.ndmap(np.asarray(mo) * taper, wo))[0]
+        want = np.array([ob.bin(p2o[a, c] if pol else p2o)[1] for a, c in pairs])
+        for s, (a, c) in enumerate(pairs):
+            scale = np.sqrt(np.abs(want[auto[a] if pol else 0] * want[auto[c] if pol else 0]))
+            ok = np.isfinite(want[s])
+            assert np.max(np.abs(bp[i, s] - want[s])[ok] / scale[ok]) < TOL64
