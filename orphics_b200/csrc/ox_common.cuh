@@ -189,6 +189,8 @@ struct ox_pipeline {
   ox_binner *b = nullptr;
   ox::DevBuf window;  // T[ny][nx] or empty
   bool has_window = false;
+  ox::DevBuf win_x, win_y;  // float64 profiles of a separable window (window == outer(win_y, win_x) exactly), else empty
+  bool win_separable = false;
   bool maps_valid = false;  // the last run left its real-space maps in s->maps
   int nspec = 1, nbins = 0, dim = 0;
   ox::DevBuf partial, bp;            // partial sums, bandpowers [max_batch][nspec][nbins]

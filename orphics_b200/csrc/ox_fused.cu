@@ -705,6 +705,10 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
     ra.map_out = s->maps.as<T>();
   }
   ra.window = pl->has_window ? pl->window.as<T>() : nullptr;
+  if (pl->has_window && pl->win_separable) {
+    ra.win_x = pl->win_x.as<double>();
+    ra.win_y = pl->win_y.as<double>();
+  }
   ra.tw = fs.tw.as<T2>();
   ra.tw_len = fs.tw_len;
   ra.ny = g->ny; ra.nx = g->nx; ra.mx = g->nx / 2;

@@ -135,6 +135,10 @@ struct RowArgs {
   // once per launch instead of once per plane (ncu round 1: 66 MB read per 33.5 MB map with rows fastest);
   // 0 = rows fastest, blockIdx.y = plane (ORPHX_KB_ORDER=rows)
   int nplanes_fast = 0;
+  // separable window (full pass only): window[iy][ix] = fl(win_y[iy] * win_x[ix]) exactly, e.g. the reference's
+  // cosine taper (maps.py:1893-1920).  The row kernel then reads the 8*nx-byte x profile (L1-resident) and one
+  // scalar per row instead of streaming the 8*ny*nx-byte window through L2 for every plane.
+  const double *win_x = nullptr, *win_y = nullptr;
 };
 
 // first-stage input of the c2r transform: Z[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/Nx} (X[k] - conj X[M-k])
@@ -174,6 +178,8 @@ struct WindowKeep {
   const T2 *win_row; // global or null
   int u;             // thread index within the row
   T2 *w;             // registers [16]: window operands in flight (only a butterfly's worth is live at a time)
+  const double2 *winx = nullptr;  // separable window: x profile as pairs (RUNTIME mode), times wy
+  double wy = 0.0;
   // RUNTIME: test the pointers per element instead of the compile-time flags.  The branches keep the
   // compiler from issuing all 16 window loads at once, which is what the full c2r -> taper -> r2c pass
   // wants (it has no registers to spare: hoisting spilled 40 B/thread and cost 15%); the one-way passes
@@ -193,7 +199,11 @@ struct WindowKeep {
   }
   __device__ __forceinline__ void operator()(int n, T2 z, int m) const {
     if (RUNTIME ? map_row != nullptr : OUT_MAP) st_once(map_row + n, z);
-    if (RUNTIME ? win_row != nullptr : WIN) {
+    if (RUNTIME && winx != nullptr) {
+      const double2 p = __ldg(winx + n);
+      z.x *= (T)(p.x * wy);   // the window value itself is formed in float64 and rounded once, as numpy forms it
+      z.y *= (T)(p.y * wy);
+    } else if (RUNTIME ? win_row != nullptr : WIN) {
       T2 w1 = ldg2(win_row + n);
       z.x *= w1.x;
       z.y *= w1.y;
@@ -243,6 +253,10 @@ fused_row_kernel(RowArgs<T> a) {
   wst.map_row = (RT ? a.map_out != nullptr : OUT_MAP) ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
   const long long grp = plane / a.group, sub = plane - grp * a.group;
   wst.win_row = (RT ? a.window != nullptr : WIN) ? reinterpret_cast<const T2 *>(a.window + grp * a.win_group_stride) + rowoff : nullptr;
+  if (RT && a.win_x != nullptr) {
+    wst.winx = reinterpret_cast<const double2 *>(a.win_x);
+    wst.wy = a.win_y[iy0 + f];
+  }
   if (IN_H) {
     // tile load: for each ix the R rows are R*16 B contiguous in the transposed layout
     const T2 *src = a.Hin + plane * (long long)(MX + 1) * a.ny + iy0;
@@ -365,7 +379,7 @@ int launch_row_mode(RowArgs<T> &a, long long nplanes) {
     grid = dim3((unsigned)((a.ny / R) * nplanes), 1);
   }
   const size_t wbytes = sizeof(T) * (size_t)a.ny * a.nx;
-  if (a.window && a.win_group_stride == 0 && nplanes > 1 && l2_persist_budget() >= wbytes) {
+  if (a.window && !a.win_x && a.win_group_stride == 0 && nplanes > 1 && l2_persist_budget() >= wbytes) {
     // the window is shared by every plane of the launch but is evicted from L2 between its uses by the
     // planes streaming through (ncu: K_B re-read its 32 MB from DRAM for every map): keep it resident
     cudaLaunchConfig_t cfg = {};

@@ -63,6 +63,42 @@ int ox_pipeline_create(ox_simplan *s, ox_powerplan *p, ox_binner *b, const doubl
     if ((st = cast_from_f64((const double *)d, pl->window.p, (long long)n, s->dtype)) != OX_OK) return fail(st);
     if (cudaStreamSynchronize(g_stream) != cudaSuccess) { set_error("window upload failed"); return fail(OX_ERR_CUDA); }
     pl->has_window = true;
+    // separable?  The reference's taper (get_taper / cosine_window, maps.py:1873-1920) is an outer product of two
+    // 1-D profiles.  Accept the fast path only if window[iy][ix] == fl(wy[iy] * wx[ix]) for EVERY pixel, with the
+    // profiles read off the row and column through a pixel where the window is exactly 1.
+    {
+      const int ny = s->g->ny, nx = s->g->nx;
+      std::vector<double> hw;
+      const double *w = window;
+      if (window_where != OX_HOST) {
+        hw.resize(n);
+        if (cudaMemcpy(hw.data(), window, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("window download failed"); return fail(OX_ERR_CUDA); }
+        w = hw.data();
+      }
+      const int r0 = ny / 2, c0 = nx / 2;
+      bool sep = !(getenv("ORPHX_WINDOW_SEPARABLE") && getenv("ORPHX_WINDOW_SEPARABLE")[0] == '0') && w[(size_t)r0 * nx + c0] == 1.0;
+      std::vector<double> wy(ny), wx(nx);
+      if (sep) {
+        for (int iy = 0; iy < ny; iy++) wy[iy] = w[(size_t)iy * nx + c0];
+        for (int ix = 0; ix < nx; ix++) wx[ix] = w[(size_t)r0 * nx + ix];
+        for (int iy = 0; iy < ny && sep; iy++) {
+          const double *row = w + (size_t)iy * nx;
+          const double y = wy[iy];
+          for (int ix = 0; ix < nx; ix++)
+            if (row[ix] != y * wx[ix]) { sep = false; break; }
+        }
+      }
+      if (sep) {
+        if ((st = pl->win_x.ensure(sizeof(double) * nx)) != OX_OK) return fail(st);
+        if ((st = pl->win_y.ensure(sizeof(double) * ny)) != OX_OK) return fail(st);
+        if (cudaMemcpy(pl->win_x.p, wx.data(), sizeof(double) * nx, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(pl->win_y.p, wy.data(), sizeof(double) * ny, cudaMemcpyHostToDevice) != cudaSuccess) {
+          set_error("window profile upload failed");
+          return fail(OX_ERR_CUDA);
+        }
+        pl->win_separable = true;
+      }
+    }
   }
   size_t d = pl->dim;
   if ((st = pl->stat.ensure(sizeof(double) * (1 + d + d * d))) != OX_OK) return fail(st);

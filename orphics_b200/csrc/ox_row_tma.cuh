@@ -129,13 +129,9 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
   // slots aligned to 1024 B (the swizzle pattern repeats every 512 B of shared-memory address)
   unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
   RowTmaCtl *ctl = reinterpret_cast<RowTmaCtl *>(base + 3 * Cfg::SLOT);
-  const int tid = threadIdx.x;
-  const int g = tid / GROUP, gt = tid - g * GROUP;   // group, thread within the group
-  const int f = gt / NT, u = gt - f * NT;            // row within the tile, thread within the row
-  const int grp_bar = 1 + g, row_bar = 3 + g * R + f;
-  const unsigned tile_bytes = (unsigned)Cfg::TILE;
-
-  auto issue = [&](int slot, int i) {   // one thread: fetch the i-th tile of this CTA into `slot` (or mark the end)
+  // one thread: fetch the i-th tile of this CTA into `slot` (or mark the end of the CTA's tiles)
+  auto issue = [&a, &tmap, nplanes, ntiles](unsigned char *base, RowTmaCtl *ctl, int slot, int i) {
+    const unsigned tile_bytes = (unsigned)Cfg::TILE;
     const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
     if (t >= ntiles) {
       ctl->tile_of[slot] = -1;
@@ -155,16 +151,16 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     bulk_load(dst + (size_t)MX * R * 16, nyq, R * 16, &ctl->full[slot]);
   };
 
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     for (int b = 0; b < 3; b++) {
       mbar_init(&ctl->full[b], 1);
       ctl->nloads[b] = 0;
     }
     fence_mbar_init();
     fence_proxy_async();
-    issue(0, 0);
-    issue(1, 1);
-    issue(2, 2);
+    issue(base, ctl, 0, 0);
+    issue(base, ctl, 1, 1);
+    issue(base, ctl, 2, 2);
     ctl->issued = 3;
     ctl->next_buf = 2;
     for (int q = 0; q < 2; q++) {
@@ -175,45 +171,63 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
   }
   __syncthreads();
 
-  typename FFT::Twiddles tws;
-  tws.init(a.tw, a.tw_len / MX, u);
-  const int tws_n = a.tw_len / NX;  // stride for exp(-2 pi i k / Nx)
-  T2 wu = a.tw[u * tws_n];
-  wu.y = -wu.y;  // e^{+2 pi i u/Nx}
-
   while (true) {
-    const int slot = ctl->grp_slot[g], t = ctl->grp_tile[g];
-    const unsigned par = (unsigned)ctl->grp_par[g];
+    // Everything is rebuilt from the thread index every iteration (it passes through an empty asm so that the
+    // compiler can neither hoist the dozens of derived addresses out of the loop nor keep them live across the
+    // transforms: with the register file full, hoisted invariants came back from local memory -- L2 round trips --
+    // inside every transform)
+    int tid = threadIdx.x;
+    asm volatile("" : "+r"(tid));
+    const int g = tid / GROUP, gt = tid - g * GROUP;
+    const int f = gt / NT, u = gt - f * NT;
+    const int grp_bar = 1 + g, row_bar = 3 + g * R + f;
+    const int tws_n = a.tw_len / NX;  // stride for exp(-2 pi i k / Nx)
+    unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
+    RowTmaCtl *ctl = reinterpret_cast<RowTmaCtl *>(base + 3 * Cfg::SLOT);
+    typename FFT::Twiddles tws;
+    tws.init(a.tw, a.tw_len / MX, u);
+    const int slot = ctl->grp_slot[g];
+    int t = ctl->grp_tile[g];
     if (t < 0) break;
-    const int rowtile = t / nplanes;
-    const long long plane = t - (long long)rowtile * nplanes;
-    const int iy0 = rowtile * R;
     T2 *s = reinterpret_cast<T2 *>(base + slot * Cfg::SLOT);
     T2 *row = s + f * PS;
-    const long long rowoff = (long long)(iy0 + f) * MX;
     T2 keep[16];
-    T2 wpf[16];
-    constexpr bool RT = OUT_H;  // the full pass takes map_out / window as run-time options
-    WindowKeep<T, OUT_MAP, WIN, RT, NT> wst;
-    wst.keep = keep;
-    wst.w = wpf;
-    wst.u = u;
-    wst.map_row = (RT ? a.map_out != nullptr : OUT_MAP) ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
-    const long long grp = plane / a.group;
-    wst.win_row = (RT ? a.window != nullptr : WIN) ? reinterpret_cast<const T2 *>(a.window + grp * a.win_group_stride) + rowoff : nullptr;
-
-    mbar_wait(&ctl->full[slot], par);   // the TMA has delivered the tile
     {
+      const int rowtile = t / nplanes;
+      const long long plane = t - (long long)rowtile * nplanes;
+      const int iy0 = rowtile * R;
+      const long long rowoff = (long long)(iy0 + f) * MX;
+      T2 wpf[16];
+      constexpr bool RT = OUT_H;  // the full pass takes map_out / window as run-time options
+      WindowKeep<T, OUT_MAP, WIN, RT, NT> wst;
+      wst.keep = keep;
+      wst.w = wpf;
+      wst.u = u;
+      wst.map_row = (RT ? a.map_out != nullptr : OUT_MAP) ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
+      const long long grp = plane / a.group;
+      wst.win_row = (RT ? a.window != nullptr : WIN) ? reinterpret_cast<const T2 *>(a.window + grp * a.win_group_stride) + rowoff : nullptr;
+      if (RT && a.win_x != nullptr) {
+        wst.winx = reinterpret_cast<const double2 *>(a.win_x);
+        wst.wy = a.win_y[iy0 + f];
+      }
+      T2 wu = a.tw[u * tws_n];
+      wu.y = -wu.y;  // e^{+2 pi i u/Nx}
+      mbar_wait(&ctl->full[slot], (unsigned)ctl->grp_par[g]);   // the TMA has delivered the tile
       PackLoadTile<T2, MX, R> ld{s, f, wu};
       // first-stage reads come from the tile (all rows interleaved) -> group-wide barrier before the writes
       FFT::template run<+1, true, false>(row, tws, u, row_bar, ld, wst, grp_bar, GROUP);
     }
     if (OUT_H) {
-      RegLoad<T2> ld{keep};
-      SmemStore<T2> st{row};
-      FFT::template run<-1, true, true>(row, tws, u, row_bar, ld, st);
+      {
+        RegLoad<T2> ld{keep};
+        SmemStore<T2> st{row};
+        FFT::template run<-1, true, true>(row, tws, u, row_bar, ld, st);
+      }
       named_sync(grp_bar, GROUP);
-      T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + iy0;
+      t = *(volatile int *)&ctl->grp_tile[g];   // (re-read: nothing of the tile's bookkeeping stays live across the transforms)
+      const int rowtile = t / nplanes;
+      const long long plane = t - (long long)rowtile * nplanes;
+      T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + rowtile * R;
 #pragma unroll 4
       for (int e = gt; e < (MX / 2 + 1) * R; e += GROUP) {
         int k = e / R, r = e - k * R;
@@ -240,9 +254,10 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
       } while (nb < 0);
       __threadfence_block();
       const int i = atomicAdd(&ctl->issued, 1);
-      issue(slot, i);
+      const int myslot = *(volatile int *)&ctl->grp_slot[g];
+      issue(base, ctl, myslot, i);
       __threadfence_block();
-      atomicExch(&ctl->next_buf, slot);
+      atomicExch(&ctl->next_buf, myslot);
       ctl->grp_slot[g] = nb;
       ctl->grp_tile[g] = ctl->tile_of[nb];
       ctl->grp_par[g] = ctl->par_of[nb];

@@ -399,11 +399,12 @@ def test_multi_pow_on_device_matches_eigpow(theory):
 
 
 @pytest.mark.parametrize("pol", [False, True])
-def test_tma_row_pass_is_bit_identical_to_the_legacy_row_pass(pol, theory, monkeypatch):
+def test_tma_row_pass_matches_the_legacy_row_pass_and_the_oracle(pol, theory, monkeypatch):
     """The persistent TMA row kernel (ox_row_tma.cuh: cp.async.bulk.tensor tiles, three slots, two groups per CTA)
-    runs the same butterflies in the same order as the one-tile-per-CTA kernel: bandpowers and stored maps must be
-    bit-identical, on a 512 x 2048 patch (nx/2 = 1024: the 2048^2 configuration's row length) -- and match the
-    oracle on numpy seeds."""
+    runs the same butterflies as the one-tile-per-CTA kernel (the compiler contracts multiply-adds differently in
+    the two instantiations, so agreement is to rounding, 1e-13, not bit for bit), on a 512 x 2048 patch (nx/2 = 1024:
+    the 2048^2 configuration's row length), with the separable-window fast path and with the general 2-D window --
+    and matches the oracle on numpy seeds."""
     from orphics_b200 import maps, stats
     ny, nx, res = 512, 2048, 1.0
     shape, wcs = maps.rect_geometry(width_arcmin=nx * res, px_res_arcmin=res, height_arcmin=ny * res, pol=pol)
@@ -415,8 +416,9 @@ def test_tma_row_pass_is_bit_identical_to_the_legacy_row_pass(pol, theory, monke
     taper = np.asarray(maps.get_taper(shape, wcs)[0])
     nsim = 5                                                     # 5 planes x 128 row tiles: odd tile counts per CTA
     out = {}
-    for kb in ("legacy", "tma"):
-        monkeypatch.setenv("ORPHX_KB", kb)
+    for kb in ("legacy", "tma", "tma_general_window"):
+        monkeypatch.setenv("ORPHX_KB", kb.split("_")[0])
+        monkeypatch.setenv("ORPHX_WINDOW_SEPARABLE", "0" if "general" in kb else "1")
         mg = maps.MapGen(shape, wcs, ps, noise="numpy", max_batch=nsim)
         fc = maps.FourierCalc(shape, wcs, max_batch=nsim)
         b = stats.bin2D(fc.geometry.modlmap(), EDGES, geometry=fc.geometry)
@@ -424,8 +426,11 @@ def test_tma_row_pass_is_bit_identical_to_the_legacy_row_pass(pol, theory, monke
         assert pipe.path == "fused"
         bp = pipe.run(range(40, 40 + nsim), keep_maps=True)
         out[kb] = (bp, pipe.last_maps(nsim))
-    assert np.array_equal(out["tma"][0], out["legacy"][0], equal_nan=True)
-    assert np.array_equal(out["tma"][1], out["legacy"][1])
+    for kb in ("tma", "tma_general_window"):
+        assert np.array_equal(np.isnan(out[kb][0]), np.isnan(out["legacy"][0]))
+        fin = np.isfinite(out["legacy"][0])
+        assert np.max(np.abs(out[kb][0] - out["legacy"][0])[fin] / np.abs(out["legacy"][0])[fin].max()) < 1e-13
+        assert relerr(out[kb][1], out["legacy"][1]) < 1e-13
     bp, stored = out["tma"]
     pairs = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)] if pol else [(0, 0)]
     auto = {0: 0, 1: 3, 2: 5}
