@@ -77,6 +77,16 @@ int ox_synchronize(void);
 int ox_set_stream(void *cuda_stream);
 int ox_malloc(void **dptr, size_t bytes);
 int ox_free(void *dptr);
+/* stream-ordered pool on the library stream (cudaMallocAsync, freed blocks are kept): the buffers behind
+ * the device-resident maps the Python mirror returns from get_map / power2d / ... (enmap.devmap) */
+int ox_malloc_pooled(void **dptr, size_t bytes);
+int ox_free_pooled(void *dptr);
+/* Elementwise arithmetic between device-resident maps -- the numpy expressions of the reference's call
+ * sequences (`imap*mask` maps.py:1359, `beamed+noise_map` lensing.py:519, `p1d/w2`): out = a (op) b, all device
+ * pointers.  kind: 0 float64, 1 float32 (a, b, out real), 2 complex128 a/out with float64 b, 3 complex64 with
+ * float32 b.  op: 0 a*b, 1 a+b, 2 a-b, 3 a/b, 4 b-a, 5 b/a (real kinds).  b == NULL: the scalar.  b has nb
+ * elements and repeats over a's n (a (ncomp,Ny,Nx) map times a (Ny,Nx) taper). */
+int ox_map_op(int op, const void *a, const void *b, double scalar, long long n, long long nb, int kind, void *out);
 int ox_memset(void *dptr, int value, size_t bytes);
 int ox_host_alloc(void **hptr, size_t bytes); /* pinned */
 int ox_host_free(void *hptr);

@@ -54,6 +54,9 @@ SIGNATURES = {
     "ox_set_stream": [_vp],
     "ox_malloc": [_pvp, _sz],
     "ox_free": [_vp],
+    "ox_malloc_pooled": [_pvp, _sz],
+    "ox_free_pooled": [_vp],
+    "ox_map_op": [_i, _vp, _vp, _d, _ll, _ll, _i, _vp],
     "ox_memset": [_vp, _i, _sz],
     "ox_host_alloc": [_pvp, _sz],
     "ox_host_free": [_vp],

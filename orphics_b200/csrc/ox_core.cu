@@ -322,6 +322,89 @@ int ox_free(void *dptr) {
   OX_CUDA(cudaFree(dptr));
   return OX_OK;
 }
+// Stream-ordered pool for the device-resident maps of the per-call API (enmap.devmap): one cudaMalloc per map
+// returned would cost more than the kernels of a 2048^2 map; the pool keeps freed blocks (release threshold =
+// never) and hands them out again without a device synchronisation.
+int ox_malloc_pooled(void **dptr, size_t bytes) {
+  OX_REQUIRE(dptr, "null pointer");
+  static int pooled_dev = -1;
+  int dev = 0;
+  OX_CUDA(cudaGetDevice(&dev));
+  if (pooled_dev != dev) {
+    cudaMemPool_t pool;
+    OX_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ULL;
+    OX_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    pooled_dev = dev;
+  }
+  cudaError_t e = cudaMallocAsync(dptr, bytes ? bytes : 1, g_stream);
+  if (e != cudaSuccess) {
+    set_error("cudaMallocAsync of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return OX_ERR_NOMEM;
+  }
+  return OX_OK;
+}
+int ox_free_pooled(void *dptr) {
+  if (dptr) OX_CUDA(cudaFreeAsync(dptr, g_stream));
+  return OX_OK;
+}
+
+namespace {
+// out[i] = a[i] (op) b[i % nb]  (or the scalar when b == null); complex a / out with a real b
+template <typename TA, typename TB>
+__global__ void map_op_kernel(int op, const TA *__restrict__ a, const TB *__restrict__ b, double scalar, long long n,
+                              long long nb, TA *__restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const TB y = b ? b[nb == n ? i : i % nb] : (TB)scalar;
+    TA x = a[i];
+    if constexpr (sizeof(TA) == sizeof(TB)) {
+      switch (op) {
+        case 0: x = x * y; break;
+        case 1: x = x + y; break;
+        case 2: x = x - y; break;
+        case 3: x = x / y; break;
+        case 4: x = y - x; break;
+        default: x = y / x; break;
+      }
+    } else {  // complex (op) real: numpy's semantics for mul/div; add/sub touch the real part only
+      switch (op) {
+        case 0: x.x = x.x * y; x.y = x.y * y; break;
+        case 1: x.x = x.x + y; break;
+        case 2: x.x = x.x - y; break;
+        case 3: x.x = x.x / y; x.y = x.y / y; break;
+        default: x.x = y - x.x; x.y = -x.y; break;
+      }
+    }
+    out[i] = x;
+  }
+}
+}  // namespace
+
+// Elementwise arithmetic on device-resident maps (what `emap * taper`, `p2d / w2`, `map + noise` of the
+// reference's call sequences do in numpy; maps.py:1351, lensing.py:519).  kind: 0 f64, 1 f32 (a, b, out real),
+// 2 complex128 a/out with float64 b, 3 complex64 a/out with float32 b.  op: 0 a*b, 1 a+b, 2 a-b, 3 a/b, 4 b-a,
+// 5 b/a (real kinds only).  b == NULL: the scalar.  b holds nb elements and repeats over a's n (nb divides n).
+int ox_map_op(int op, const void *a, const void *b, double scalar, long long n, long long nb, int kind, void *out) {
+  OX_REQUIRE(a && out && n >= 0, "ox_map_op: null pointer");
+  OX_REQUIRE(op >= 0 && op <= 5 && kind >= 0 && kind <= 3, "ox_map_op: op=%d kind=%d", op, kind);
+  OX_REQUIRE(!(kind >= 2 && op == 5), "ox_map_op: real / complex is not provided");
+  if (b) OX_REQUIRE(nb > 0 && n % nb == 0, "ox_map_op: operand of %lld elements does not tile %lld", nb, n);
+  if (n == 0) return OX_OK;
+  const int threads = 256;
+  long long want = (n + threads - 1) / threads;
+  const int blocks = (int)(want < (long long)sm_count() * 16 ? want : (long long)sm_count() * 16);
+  switch (kind) {
+    case 0: map_op_kernel<double, double><<<blocks, threads, 0, g_stream>>>(op, (const double *)a, (const double *)b, scalar, n, nb, (double *)out); break;
+    case 1: map_op_kernel<float, float><<<blocks, threads, 0, g_stream>>>(op, (const float *)a, (const float *)b, scalar, n, nb, (float *)out); break;
+    case 2: map_op_kernel<double2, double><<<blocks, threads, 0, g_stream>>>(op, (const double2 *)a, (const double *)b, scalar, n, nb, (double2 *)out); break;
+    default: map_op_kernel<float2, float><<<blocks, threads, 0, g_stream>>>(op, (const float2 *)a, (const float *)b, scalar, n, nb, (float2 *)out); break;
+  }
+  OX_KERNEL_CHECK();
+  return OX_OK;
+}
+
 int ox_memset(void *dptr, int value, size_t bytes) {
   OX_CUDA(cudaMemsetAsync(dptr, value, bytes, g_stream));
   return OX_OK;

@@ -222,6 +222,7 @@ struct BlockFFT {
 
   struct Twiddles {
     T2 w[NW > 0 ? NW : 1];
+    __device__ __forceinline__ T2 get(int i) const { return w[i]; }
     // tw: table exp(-2 pi i j / (L*tw_stride)), j < L*tw_stride
     __device__ __forceinline__ void init(const T2 *__restrict__ tw, int tw_stride, int u) {
       int o = 0;
@@ -240,6 +241,40 @@ struct BlockFFT {
           w[o++] = tw[k * (L / (Ns * P::REM)) * tw_stride];
         }
       }
+    }
+  };
+
+  // The same first-order twiddles fetched where a stage needs them from a shared-memory table
+  // tab[j] = exp(-2 pi i j / (2L)), j <= L/4 (second octant by the exact symmetry of fused_make_twiddles' table:
+  // tab[L/2 - j] = (-Im tab[j], -Re tab[j])), instead of living in ~4 NW registers across every transform of a
+  // persistent kernel.  Needs every exponent below L/2 in units of 1/(2L): REM in {1, 4, 8}.
+  struct SmemTwiddles {
+    static constexpr bool OK = P::REM == 1 || P::REM == 4 || P::REM == 8;
+    const T2 *tab;
+    int u;
+    __device__ __forceinline__ T2 get(int i) const {
+      // i is a compile-time constant after unrolling: i < N16-1 -> radix-16 stage i+1, else butterfly q of the last stage
+      int Ns = 16, idx = 0;
+      bool found = false;
+#pragma unroll
+      for (int st = 1; st < P::N16; st++) {
+        if (i == st - 1) {
+          idx = 2 * (u & (Ns - 1)) * (L / (Ns * 16));
+          found = true;
+        }
+        Ns *= 16;
+      }
+      if (!found) {
+        const int q = i - (P::N16 > 1 ? P::N16 - 1 : 0);
+        const int j = u + q * NT;
+        idx = 2 * (j & (Ns - 1)) * (L / (Ns * (P::REM > 1 ? P::REM : 1)));
+      }
+      const bool hi = idx > L / 4;
+      const T2 t = tab[hi ? L / 2 - idx : idx];
+      T2 r;
+      r.x = hi ? -t.y : t.x;
+      r.y = hi ? -t.x : t.y;
+      return r;
     }
   };
 
@@ -276,8 +311,8 @@ struct BlockFFT {
 
   // one Stockham stage of radix R (Q = 16/R butterflies per unit), Ns = product of previous radices
   template <int DIR, int R, int Ns, int WOFF, bool FIRST, bool LAST, bool SYNC_BEFORE_WRITE, bool SYNC_AFTER_WRITE,
-            class LoadOp, class StoreOp>
-  static __device__ __forceinline__ void stage(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
+            class TW, class LoadOp, class StoreOp>
+  static __device__ __forceinline__ void stage(T2 *__restrict__ s, const TW &tws, int u, int bar, const LoadOp &ld,
                                                const StoreOp &st, int bar_bw = -1, int cnt_bw = 0) {
     constexpr int Q = 16 / R;
     constexpr bool PF = LAST && Q > 1 && has_prefetch<StoreOp>::value;
@@ -293,7 +328,7 @@ struct BlockFFT {
         const int e = u + (q + r * Q) * NT;  // = j + r*L/R with j = u + q*NT
         v[q * R + r] = FIRST ? ld(e, q + r * Q) : s[pad(e)];
       }
-      if (Ns > 1) apply_twiddles<DIR, R>(&v[q * R], tws.w[WOFF + q]);
+      if (Ns > 1) apply_twiddles<DIR, R>(&v[q * R], tws.get(WOFF + q));
       if (R == 16) dft16<DIR>(&v[0]);
       if (R == 8) dft8<DIR>(&v[q * 8]);
       if (R == 4) dft4<DIR>(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
@@ -327,8 +362,8 @@ struct BlockFFT {
     if (SYNC_AFTER_WRITE) fft_sync(bar, NT);
   }
 
-  template <int DIR, int I, int Ns, bool IN_SMEM, bool OUT_SMEM, class LoadOp, class StoreOp>
-  static __device__ __forceinline__ void from(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
+  template <int DIR, int I, int Ns, bool IN_SMEM, bool OUT_SMEM, class TW, class LoadOp, class StoreOp>
+  static __device__ __forceinline__ void from(T2 *__restrict__ s, const TW &tws, int u, int bar, const LoadOp &ld,
                                               const StoreOp &st, int bar0 = -1, int cnt0 = 0) {
     constexpr int rem = L / Ns;
     constexpr bool first = (I == 0);
@@ -347,9 +382,9 @@ struct BlockFFT {
     }
   }
 
-  template <int DIR, bool IN_SMEM, bool OUT_SMEM, class LoadOp, class StoreOp>
+  template <int DIR, bool IN_SMEM, bool OUT_SMEM, class TW, class LoadOp, class StoreOp>
   // bar0 / cnt0: optional wider named barrier (id, thread count) fencing the FIRST stage's reads from its writes
-  static __device__ __forceinline__ void run(T2 *__restrict__ s, const Twiddles &tws, int u, int bar, const LoadOp &ld,
+  static __device__ __forceinline__ void run(T2 *__restrict__ s, const TW &tws, int u, int bar, const LoadOp &ld,
                                              const StoreOp &st, int bar0 = -1, int cnt0 = 0) {
     from<DIR, 0, 1, IN_SMEM, OUT_SMEM>(s, tws, u, bar, ld, st, bar0, cnt0);
   }

@@ -603,10 +603,38 @@ int fused_make_twiddles(int len, int dtype, DevBuf &buf) {
   OX_TRY(buf.ensure(es * len));
   std::vector<double> h(2 * (size_t)len);
   const long double tau = 6.283185307179586476925286766559005768394L;
-  for (int j = 0; j < len; j++) {
-    long double ang = -tau * (long double)j / (long double)len;
-    h[2 * j] = (double)cosl(ang);
-    h[2 * j + 1] = (double)sinl(ang);
+  if (len % 8 == 0) {
+    // first octant from the library, the rest by the exact symmetries of the circle, so that kernels may rebuild
+    // w_{len/4 - j} = (-Im w_j, -Re w_j) etc. from a part of the table and get the same bits (ox_row_tma.cuh)
+    const int o = len / 8;
+    std::vector<double> c(o + 1), sn(o + 1);
+    for (int j = 0; j <= o; j++) {
+      long double ang = tau * (long double)j / (long double)len;
+      c[j] = (double)cosl(ang);
+      sn[j] = (double)sinl(ang);
+    }
+    sn[o] = c[o];  // cos(pi/4) = sin(pi/4)
+    for (int j = 0; j < len; j++) {
+      const int q = j / (2 * o), r = j % (2 * o);   // quadrant, position inside it (angle = q pi/2 + 2 pi r/len)
+      const double cr = r <= o ? c[r] : sn[2 * o - r], sr = r <= o ? sn[r] : c[2 * o - r];
+      double cj, sj;   // cos / sin of 2 pi j / len
+      switch (q) {
+        case 0: cj = cr; sj = sr; break;
+        case 1: cj = -sr; sj = cr; break;
+        case 2: cj = -cr; sj = -sr; break;
+        default: cj = sr; sj = -cr; break;
+      }
+      h[2 * j] = cj;
+      h[2 * j + 1] = -sj;
+    }
+    for (auto &v : h)
+      if (v == 0.0) v = 0.0;    // (no negative zeros)
+  } else {
+    for (int j = 0; j < len; j++) {
+      long double ang = -tau * (long double)j / (long double)len;
+      h[2 * j] = (double)cosl(ang);
+      h[2 * j + 1] = (double)sinl(ang);
+    }
   }
   if (dtype == OX_F64) {
     OX_CUDA(cudaMemcpyAsync(buf.p, h.data(), es * len, cudaMemcpyHostToDevice, g_stream));

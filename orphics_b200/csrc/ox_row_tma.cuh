@@ -96,123 +96,155 @@ struct PackLoadTile {
   }
 };
 
-struct RowTmaCtl {
-  unsigned long long full[3];  // one mbarrier per slot: the tile's bytes have landed
-  int next_buf;                // slot holding the tile in flight / landed that nobody owns yet (-1: being handed over)
-  int issued;                  // tiles of this CTA issued so far
-  int tile_of[3], par_of[3], nloads[3];
-  int grp_slot[2], grp_tile[2], grp_par[2];
+// last-stage output of the c2r transform in the persistent kernel (see WindowKeep): store the map, apply the window
+// and keep the element in registers.  The x profile of a separable window lives in shared memory (the carve-out
+// leaves ~29 KB of L1: the 16 KB profile and the 32 KB twiddle table evicted each other and 3 of 4 table loads
+// went to L2 -- ncu round 2: 118 M sectors of table loads per launch, 26% L1 hits, long-scoreboard stalls).
+template <typename T, bool OUT_H, int NT>
+struct RowTmaStore {
+  typedef typename V2<T>::type T2;
+  T2 *keep;               // registers [16]
+  T2 *map_row;            // global or null
+  const T2 *win_row;      // global or null (general window)
+  const double2 *swinx;   // shared memory or null: x profile of a separable window as pairs, times wy
+  double wy;
+  __device__ __forceinline__ void operator()(int n, T2 z, int m) const {
+    if (!OUT_H || map_row != nullptr) st_once(map_row + n, z);
+    if (OUT_H) {
+      if (swinx != nullptr) {
+        const double2 p = swinx[n];
+        z.x *= (T)(p.x * wy);   // the window value itself is formed in float64 and rounded once, as numpy forms it
+        z.y *= (T)(p.y * wy);
+      } else if (win_row != nullptr) {
+        T2 w1 = ldg2(win_row + n);
+        z.x *= w1.x;
+        z.y *= w1.y;
+      }
+      keep[m] = z;
+    }
+  }
 };
 
 template <int MX, int R>
 struct RowTmaCfg {
   static constexpr int NT = MX / 16, GROUP = R * NT, NTHREADS = 2 * GROUP;
-  static constexpr size_t WORK = 16 * (size_t)R * padded_size(MX);        // padded per-row work area
+  // per-row work area of the FFT engine: pad(MX) + the Nyquist element, rounded up to 2 (mod 8) elements so that
+  // equal indices of neighbouring rows fall into different 16-byte bank groups (tighter than padded_size())
+  static constexpr int PS0 = MX + MX / 16 + 1, PS = PS0 + ((2 - PS0 % 8) + 8) % 8;
+  static constexpr size_t WORK = 16 * (size_t)R * PS;                      // padded work area
   static constexpr size_t TILE = 16 * (size_t)R * (MX + 1);               // raw tile
-  static constexpr size_t SLOT = (((WORK > TILE ? WORK : TILE) + 1023) / 1024) * 1024;
-  static constexpr size_t SMEM = 3 * SLOT + sizeof(RowTmaCtl) + 1024;     // (+ alignment slack)
+  static constexpr size_t SLOT = (((WORK > TILE ? WORK : TILE) + 511) / 512) * 512;  // (the swizzle pattern repeats every 512 B)
+  static constexpr size_t WINX = 8 * (size_t)(2 * MX);                    // x profile of a separable window
+  static constexpr size_t UTW = 16 * (size_t)(MX / 4 + 1);                // exp(-2 pi i k / Nx), k <= Nx/8
+  static constexpr size_t SMEM_C2R = 3 * SLOT + 64 + UTW + 1024;          // slots + mbarriers + twiddles (+ alignment slack)
+  static constexpr size_t SMEM_FULL = 3 * SLOT + 64 + UTW + WINX + 1024;
   static constexpr int BOXW = 256;                                        // columns per TMA box
   static_assert(MX % BOXW == 0, "MX must be a multiple of the TMA box width");
 };
 
 // MODE: ROW_IN_H | ROW_OUT_H (full pass; map_out / window are run-time options) or ROW_IN_H | ROW_OUT_MAP (c2r only)
+//
+// Schedule (static, no bookkeeping in memory): the CTA's i-th tile is t = blockIdx.x + i * gridDim.x; it lives in slot
+// i % 3 and is transformed by group i % 2.  The group that finishes tile i refills its slot with tile i + 3 (which
+// the OTHER group will transform after its tile i + 1) and moves on to tile i + 2, whose load was started a tile
+// and a half earlier.  The k-th fill of a slot completes phase k of the slot's mbarrier.
 template <typename T, int MX, int R, int MODE>
-__global__ void __launch_bounds__(RowTmaCfg<MX, R>::NTHREADS, (RowTmaCfg<MX, R>::NTHREADS <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(RowTmaCfg<MX, R>::NTHREADS, 1)
 fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int nplanes, int ntiles) {
   static_assert(sizeof(T) == 8, "the TMA row pass is written for 16-byte elements");
-  constexpr bool OUT_MAP = MODE & ROW_OUT_MAP, WIN = MODE & ROW_WIN, OUT_H = MODE & ROW_OUT_H;
+  constexpr bool OUT_H = MODE & ROW_OUT_H;
   typedef typename V2<T>::type T2;
   typedef BlockFFT<T, MX> FFT;
   typedef RowTmaCfg<MX, R> Cfg;
-  constexpr int NT = Cfg::NT, GROUP = Cfg::GROUP, PS = padded_size(MX), NX = 2 * MX;
+  constexpr int NT = Cfg::NT, GROUP = Cfg::GROUP, PS = Cfg::PS, NX = 2 * MX;
   extern __shared__ unsigned char smem_dyn[];
-  // slots aligned to 1024 B (the swizzle pattern repeats every 512 B of shared-memory address)
-  unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
-  RowTmaCtl *ctl = reinterpret_cast<RowTmaCtl *>(base + 3 * Cfg::SLOT);
-  // one thread: fetch the i-th tile of this CTA into `slot` (or mark the end of the CTA's tiles)
-  auto issue = [&a, &tmap, nplanes, ntiles](unsigned char *base, RowTmaCtl *ctl, int slot, int i) {
-    const unsigned tile_bytes = (unsigned)Cfg::TILE;
+  // one thread: fetch the i-th tile of this CTA into slot i % 3 (nothing to do past the CTA's last tile)
+  auto issue = [&a, &tmap, nplanes, ntiles](unsigned char *base, int i) {
     const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
-    if (t >= ntiles) {
-      ctl->tile_of[slot] = -1;
-      return;
-    }
+    if (t >= ntiles) return;
     const int rowtile = (int)(t / nplanes), plane = (int)(t - (long long)rowtile * nplanes);
-    ctl->tile_of[slot] = (int)t;
-    ctl->par_of[slot] = ctl->nloads[slot] & 1;
-    ctl->nloads[slot]++;
+    const int slot = i % 3;
     unsigned char *dst = base + slot * Cfg::SLOT;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot;
     fence_proxy_async();   // the slot was last written through the generic proxy (the FFT work area)
-    mbar_expect_tx(&ctl->full[slot], tile_bytes);
+    mbar_expect_tx(bar, (unsigned)Cfg::TILE);
 #pragma unroll
     for (int j = 0; j < MX / Cfg::BOXW; j++)
-      tma_load_3d(dst + (size_t)j * Cfg::BOXW * R * 16, &tmap, 2 * rowtile * R, j * Cfg::BOXW, plane, &ctl->full[slot]);
+      tma_load_3d(dst + (size_t)j * Cfg::BOXW * R * 16, &tmap, 2 * rowtile * R, j * Cfg::BOXW, plane, bar);
     const T2 *nyq = a.Hin + ((long long)plane * (MX + 1) + MX) * a.ny + rowtile * R;
-    bulk_load(dst + (size_t)MX * R * 16, nyq, R * 16, &ctl->full[slot]);
+    bulk_load(dst + (size_t)MX * R * 16, nyq, R * 16, bar);
   };
 
-  if (threadIdx.x == 0) {
-    for (int b = 0; b < 3; b++) {
-      mbar_init(&ctl->full[b], 1);
-      ctl->nloads[b] = 0;
+  {
+    // slots aligned to 1024 B; [3 slots][3 mbarriers (64 B)][twiddles][x profile of the window]
+    unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
+    if (threadIdx.x == 0) {
+      unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT);
+      for (int b = 0; b < 3; b++) mbar_init(bars + b, 1);
+      fence_mbar_init();
+      issue(base, 0);
+      issue(base, 1);
+      issue(base, 2);
     }
-    fence_mbar_init();
-    fence_proxy_async();
-    issue(base, ctl, 0, 0);
-    issue(base, ctl, 1, 1);
-    issue(base, ctl, 2, 2);
-    ctl->issued = 3;
-    ctl->next_buf = 2;
-    for (int q = 0; q < 2; q++) {
-      ctl->grp_slot[q] = q;
-      ctl->grp_tile[q] = ctl->tile_of[q];
-      ctl->grp_par[q] = ctl->par_of[q];
+    T2 *utw = reinterpret_cast<T2 *>(base + 3 * Cfg::SLOT + 64);
+    const int tws_n = a.tw_len / NX;
+    for (int e = threadIdx.x; e <= MX / 4; e += Cfg::NTHREADS) utw[e] = a.tw[e * tws_n];
+    if (OUT_H && a.win_x != nullptr) {
+      double *swx = reinterpret_cast<double *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW);
+      for (int e = threadIdx.x; e < NX; e += Cfg::NTHREADS) swx[e] = a.win_x[e];
     }
+    __syncthreads();
   }
-  __syncthreads();
 
-  while (true) {
-    // Everything is rebuilt from the thread index every iteration (it passes through an empty asm so that the
+  for (int i = threadIdx.x / GROUP;; i += 2) {
+    // Everything but i is rebuilt from the thread index every iteration (it passes through an empty asm so that the
     // compiler can neither hoist the dozens of derived addresses out of the loop nor keep them live across the
-    // transforms: with the register file full, hoisted invariants came back from local memory -- L2 round trips --
-    // inside every transform)
+    // transforms: with the register file full, hoisted invariants came back from local memory inside every transform)
     int tid = threadIdx.x;
     asm volatile("" : "+r"(tid));
     const int g = tid / GROUP, gt = tid - g * GROUP;
     const int f = gt / NT, u = gt - f * NT;
     const int grp_bar = 1 + g, row_bar = 3 + g * R + f;
-    const int tws_n = a.tw_len / NX;  // stride for exp(-2 pi i k / Nx)
+    __builtin_assume(row_bar > 0);   // (the engine's barrier 0 = __syncthreads is never used here)
+    const int t = blockIdx.x + i * gridDim.x;   // (ntiles + gridDim.x < 2^31, checked by the launcher)
+    if (t >= ntiles) break;
     unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
-    RowTmaCtl *ctl = reinterpret_cast<RowTmaCtl *>(base + 3 * Cfg::SLOT);
-    typename FFT::Twiddles tws;
-    tws.init(a.tw, a.tw_len / MX, u);
-    const int slot = ctl->grp_slot[g];
-    int t = ctl->grp_tile[g];
-    if (t < 0) break;
+    const int slot = i % 3;
     T2 *s = reinterpret_cast<T2 *>(base + slot * Cfg::SLOT);
     T2 *row = s + f * PS;
+    // twiddles: fetched per stage from the shared-memory table where the plan allows it (frees ~20 registers
+    // that otherwise live across both transforms; with them the kernel spilled 84 B / thread)
+    constexpr bool STW = FFT::SmemTwiddles::OK;
+    typename std::conditional<STW, typename FFT::SmemTwiddles, typename FFT::Twiddles>::type tws;
+    if constexpr (STW) {
+      tws.tab = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64);
+      tws.u = u;
+    } else {
+      tws.init(a.tw, a.tw_len / MX, u);
+    }
+    const int rowtile = t / nplanes;
+    const long long plane = t - rowtile * nplanes;
     T2 keep[16];
     {
-      const int rowtile = t / nplanes;
-      const long long plane = t - (long long)rowtile * nplanes;
       const int iy0 = rowtile * R;
       const long long rowoff = (long long)(iy0 + f) * MX;
-      T2 wpf[16];
-      constexpr bool RT = OUT_H;  // the full pass takes map_out / window as run-time options
-      WindowKeep<T, OUT_MAP, WIN, RT, NT> wst;
+      RowTmaStore<T, OUT_H, NT> wst;
       wst.keep = keep;
-      wst.w = wpf;
-      wst.u = u;
-      wst.map_row = (RT ? a.map_out != nullptr : OUT_MAP) ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
-      const long long grp = plane / a.group;
-      wst.win_row = (RT ? a.window != nullptr : WIN) ? reinterpret_cast<const T2 *>(a.window + grp * a.win_group_stride) + rowoff : nullptr;
-      if (RT && a.win_x != nullptr) {
-        wst.winx = reinterpret_cast<const double2 *>(a.win_x);
-        wst.wy = a.win_y[iy0 + f];
+      wst.map_row = a.map_out != nullptr ? reinterpret_cast<T2 *>(a.map_out + plane * (long long)a.ny * NX) + rowoff : nullptr;
+      wst.win_row = nullptr;
+      wst.swinx = nullptr;
+      wst.wy = 0.0;
+      if (OUT_H) {
+        if (a.win_x != nullptr) {
+          wst.swinx = reinterpret_cast<const double2 *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW);
+          wst.wy = a.win_y[iy0 + f];
+        } else if (a.window != nullptr) {
+          wst.win_row = reinterpret_cast<const T2 *>(a.window + (plane / a.group) * a.win_group_stride) + rowoff;
+        }
       }
-      T2 wu = a.tw[u * tws_n];
+      T2 wu = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64)[u];   // (u < MX/16: inside the table)
       wu.y = -wu.y;  // e^{+2 pi i u/Nx}
-      mbar_wait(&ctl->full[slot], (unsigned)ctl->grp_par[g]);   // the TMA has delivered the tile
+      mbar_wait(reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot, (unsigned)((i / 3) & 1));  // the tile has landed
       PackLoadTile<T2, MX, R> ld{s, f, wu};
       // first-stage reads come from the tile (all rows interleaved) -> group-wide barrier before the writes
       FFT::template run<+1, true, false>(row, tws, u, row_bar, ld, wst, grp_bar, GROUP);
@@ -224,16 +256,20 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
         FFT::template run<-1, true, true>(row, tws, u, row_bar, ld, st);
       }
       named_sync(grp_bar, GROUP);
-      t = *(volatile int *)&ctl->grp_tile[g];   // (re-read: nothing of the tile's bookkeeping stays live across the transforms)
-      const int rowtile = t / nplanes;
-      const long long plane = t - (long long)rowtile * nplanes;
+      // transposed store with the r2c unpacking fused in (see fused_row_kernel); w_k from the shared-memory table,
+      // second octant by symmetry: w_{Nx/4 - j} = (-Im w_j, -Re w_j) (exact: fused_make_twiddles builds it that way)
+      const T2 *utw = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64);
       T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + rowtile * R;
 #pragma unroll 4
       for (int e = gt; e < (MX / 2 + 1) * R; e += GROUP) {
-        int k = e / R, r = e - k * R;
+        const int k = e / R, r = e - k * R;
         const T2 *zr = s + r * PS;
-        T2 zk = zr[pad(k)], zm = zr[pad(k == 0 ? 0 : MX - k)];
-        T2 w = ldg2(a.tw + k * tws_n);
+        const T2 zk = zr[pad(k)], zm = zr[pad(k == 0 ? 0 : MX - k)];
+        const bool hi = k > MX / 4;
+        const T2 wj = utw[hi ? MX / 2 - k : k];
+        T2 w;
+        w.x = hi ? -wj.y : wj.x;
+        w.y = hi ? -wj.x : wj.y;
         T2 sum = cadd(zk, cconj(zm)), dif = csub(zk, cconj(zm));
         T2 pw = mul_i<+1>(cmul(w, dif));
         T2 x0, x1;
@@ -245,24 +281,9 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
         if (2 * k != MX) st_once(dst + (long long)(MX - k) * a.ny + r, x1);
       }
     }
-    // everybody in the group is done with the slot: hand it to the TMA, take over the prefetched one
+    // everybody in the group is done with the slot: one thread refills it, nobody waits for that
     named_sync(grp_bar, GROUP);
-    if (gt == 0) {
-      int nb;
-      do {
-        nb = atomicExch(&ctl->next_buf, -1);
-      } while (nb < 0);
-      __threadfence_block();
-      const int i = atomicAdd(&ctl->issued, 1);
-      const int myslot = *(volatile int *)&ctl->grp_slot[g];
-      issue(base, ctl, myslot, i);
-      __threadfence_block();
-      atomicExch(&ctl->next_buf, myslot);
-      ctl->grp_slot[g] = nb;
-      ctl->grp_tile[g] = ctl->tile_of[nb];
-      ctl->grp_par[g] = ctl->par_of[nb];
-    }
-    named_sync(grp_bar, GROUP);
+    if (gt == 0) issue(base, i + 3);
   }
 }
 
@@ -296,10 +317,13 @@ int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
   if constexpr (sizeof(T) == 8 && (MODE == (ROW_IN_H | ROW_OUT_H) || MODE == (ROW_IN_H | ROW_OUT_MAP)) && (MX / 16) % 32 == 0) {
     constexpr int R = RowCfg<T, MX>::R;
     typedef RowTmaCfg<MX, R> Cfg;
-    if constexpr (Cfg::SMEM <= SMEM_MAX && Cfg::NTHREADS <= 1024 && (R == 1 || R == 2 || R == 4)) {
+    constexpr size_t SMEM = (MODE & ROW_OUT_H) ? Cfg::SMEM_FULL : Cfg::SMEM_C2R;
+    // (R = 2, the 32-byte segments of nx = 4096 in 70 KB slots, measured slower than the one-tile kernel: 2.05 vs
+    // 1.72 ms for the estimator's c2r pass -- the TMA unit is fed 32 B box rows)
+    if constexpr (SMEM <= SMEM_MAX && Cfg::NTHREADS <= 1024 && R == 4) {
       if (!row_tma_enabled() || !tma_encoder() || a.ny % R != 0) return OX_OK;
       const long long ntiles = (long long)(a.ny / R) * nplanes;
-      if (ntiles >= (1LL << 31) || nplanes >= (1LL << 31)) return OX_OK;
+      if (ntiles >= (1LL << 30) || nplanes >= (1LL << 30)) return OX_OK;
       // the transposed half planes as a 3-D tensor of doubles: [plane][ix = 0..MX][2 * ny]
       CUtensorMap tmap;
       cuuint64_t dims[3] = {(cuuint64_t)2 * a.ny, (cuuint64_t)MX + 1, (cuuint64_t)nplanes};
@@ -315,13 +339,11 @@ int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
         return OX_ERR_CUDA;
       }
       auto k = fused_row_tma_kernel<T, MX, R, MODE>;
-      OX_TRY(set_smem(k, Cfg::SMEM));
-      // one persistent CTA per SM (two where 256-thread CTAs and their three slots fit twice)
-      const int per_sm = (Cfg::NTHREADS <= 256 && 2 * Cfg::SMEM <= SMEM_MAX) ? 2 : 1;
-      int grid = sm_count() * per_sm;
+      OX_TRY(set_smem(k, SMEM));
+      int grid = sm_count();   // one persistent CTA per SM
       if ((long long)grid * 2 > ntiles) grid = (int)((ntiles + 1) / 2);
       a.nplanes_fast = (int)nplanes;
-      k<<<grid, Cfg::NTHREADS, Cfg::SMEM, g_stream>>>(a, tmap, (int)nplanes, (int)ntiles);
+      k<<<grid, Cfg::NTHREADS, SMEM, g_stream>>>(a, tmap, (int)nplanes, (int)ntiles);
       OX_KERNEL_CHECK();
       *launched = true;
     }

@@ -7,6 +7,7 @@ Reference call sites: enmap.geometry maps.py:1490; enmap.area maps.py:1567,1605;
 enmap.lmap/modlmap/laxes maps.py:1374,1607,1938-1939.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -59,6 +60,281 @@ class ndmap(np.ndarray):
     def __array_finalize__(self, obj):
         if obj is not None:
             self.wcs = getattr(obj, "wcs", None)
+
+
+#: True: the per-pixel results of the reference-signature calls (MapGen.get_map, FourierCalc.iqu2teb / fft / ifft /
+#: f2power / power2d, filter_map, get_taper, qest.kappa_from_map) come back as ``devmap``: arrays that live in HBM,
+#: are accepted as such by every one of those calls and by bin2D.bin, and turn into the numpy ``ndmap`` the
+#: reference returns on first host access.  ORPHX_DEVICE_MAPS=0 restores plain host ndmaps.
+DEVICE_RESIDENT = os.environ.get("ORPHX_DEVICE_MAPS", "1") != "0"
+
+
+class _PoolBuf:
+    """Owner of one block of the library's stream-ordered device pool (ox_malloc_pooled)."""
+    __slots__ = ("ptr", "nbytes")
+
+    def __init__(self, nbytes):
+        _capi.require_device()
+        p = C.c_void_p()
+        check(lib.ox_malloc_pooled(C.byref(p), int(nbytes)))
+        self.ptr = p.value
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib.ox_free_pooled(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+_OPS = {"mul": 0, "add": 1, "sub": 2, "div": 3, "rsub": 4, "rdiv": 5}
+_UFUNC_OPS = {np.multiply: "mul", np.add: "add", np.subtract: "sub", np.true_divide: "div"}
+_REFLECT = {"mul": "mul", "add": "add", "sub": "rsub", "div": "rdiv"}
+
+
+class devmap(object):
+    """A map that lives in device memory and stands in for the ``ndmap`` the reference returns
+    (maps.py:1585-1587, 1617, 1677): shape / dtype / wcs / indexing / arithmetic as numpy has them.
+
+    * Handed to another call of this package (power2d, f2power, ifft, filter_map, bin2D.bin, kappa_from_map, ...)
+      it is consumed where it is: no PCIe transfer.
+    * ``emap * taper``, ``a + b``, ``p2d / w2`` between devmaps (or with scalars / host arrays) run on the device
+      (ox_map_op) and return devmaps.
+    * Anything else -- np.asarray, slicing, reductions, attribute access -- materialises the host copy once
+      (``__array__``) and behaves as the numpy ndmap; results of such operations are host ndmaps.
+    devmaps are immutable on the device: item assignment edits the host copy and re-uploads on next device use."""
+
+    __array_priority__ = 1000.0
+
+    def __init__(self, owner, ptr_, shape, dtype, wcs=None, host=None):
+        self._owner = owner          # _PoolBuf (shared by views) or None when only the host copy exists
+        self._ptr = ptr_
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(dtype)
+        self.wcs = wcs
+        self._host = host            # ndmap or None
+        self._dev_valid = ptr_ is not None
+
+    # ---- construction
+    @classmethod
+    def empty(cls, shape, dtype, wcs=None):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        buf = _PoolBuf(n)
+        return cls(buf, buf.ptr, shape, dtype, wcs)
+
+    @classmethod
+    def from_host(cls, arr, wcs=None):
+        """Both copies valid: the array is uploaded now and kept as the host view."""
+        wcs = getattr(arr, "wcs", None) if wcs is None else wcs
+        a = np.ascontiguousarray(arr)
+        out = cls.empty(a.shape, a.dtype, wcs)
+        check(lib.ox_memcpy_h2d(C.c_void_p(out._ptr), ptr(a), a.nbytes))
+        out._host = ndmap(a, wcs)
+        return out
+
+    # ---- numpy-like surface
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64))
+
+    @property
+    def nbytes(self):
+        return self.size * self.dtype.itemsize
+
+    @property
+    def ptr(self):
+        """Device address (uploads the host copy first if that is the newer one)."""
+        if not self._dev_valid:
+            a = np.ascontiguousarray(self._host)
+            if self._owner is None or self._owner.nbytes < a.nbytes:
+                self._owner = _PoolBuf(a.nbytes)
+                self._ptr = self._owner.ptr
+            check(lib.ox_memcpy_h2d(C.c_void_p(self._ptr), ptr(a), a.nbytes))
+            self._dev_valid = True
+        return self._ptr
+
+    def host(self):
+        """The numpy ndmap (device -> host once, then cached)."""
+        if self._host is None:
+            out = np.empty(self.shape, dtype=self.dtype)
+            check(lib.ox_memcpy_d2h(ptr(out), C.c_void_p(self._ptr), out.nbytes))
+            self._host = ndmap(out, self.wcs)
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        h = self.host()
+        if dtype is not None and np.dtype(dtype) != h.dtype:
+            return np.asarray(h).astype(dtype)
+        return np.array(h, copy=True) if copy else np.asarray(h)
+
+    def __len__(self):
+        if not self.shape:
+            raise TypeError("len() of unsized object")
+        return self.shape[0]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __getitem__(self, idx):
+        # a leading-axis integer (kmapTEB[0], maps[i]) is a view of the same device block; anything else is numpy's
+        if isinstance(idx, (int, np.integer)) and self.ndim >= 1 and self._dev_valid and self.ndim > 2:
+            i = int(idx)
+            if i < 0:
+                i += self.shape[0]
+            if not 0 <= i < self.shape[0]:
+                raise IndexError(f"index {idx} is out of bounds for axis 0 with size {self.shape[0]}")
+            sub = self.shape[1:]
+            step = int(np.prod(sub, dtype=np.int64)) * self.dtype.itemsize
+            h = None if self._host is None else self._host[i]
+            return devmap(self._owner, self._ptr + i * step, sub, self.dtype, self.wcs, host=h)
+        return self.host()[idx]
+
+    def __setitem__(self, idx, value):
+        h = self.host()
+        h[idx] = value
+        self._dev_valid = False      # the host copy is now the newer one
+        if self._owner is not None and self._ptr != self._owner.ptr:
+            self._owner = None       # (a view: never write through into the parent's block)
+
+    def copy(self):
+        out = devmap.empty(self.shape, self.dtype, self.wcs)
+        check(lib.ox_memcpy_d2d(C.c_void_p(out._ptr), C.c_void_p(self.ptr), self.nbytes))
+        return out
+
+    def reshape(self, *shape):
+        shape = shape[0] if len(shape) == 1 and not isinstance(shape[0], (int, np.integer)) else shape
+        shape = tuple(int(v) for v in shape)
+        if -1 in shape:
+            known = -int(np.prod(shape, dtype=np.int64))
+            shape = tuple(self.size // known if v == -1 else v for v in shape)
+        if int(np.prod(shape, dtype=np.int64)) != self.size:
+            raise ValueError(f"cannot reshape array of size {self.size} into shape {shape}")
+        if not self._dev_valid:
+            return self.host().reshape(shape)
+        return devmap(self._owner, self._ptr, shape, self.dtype, self.wcs,
+                      host=None if self._host is None else self._host.reshape(shape))
+
+    def __getattr__(self, name):
+        # everything numpy offers that is not provided above (mean, sum, real, T, astype, ...) -> the host ndmap
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.host(), name)
+
+    def __repr__(self):
+        return "devmap(" + repr(self.host()) + ")"
+
+    # ---- arithmetic on the device
+    def _kind(self):
+        return {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.complex128): 2, np.dtype(np.complex64): 3}.get(self.dtype)
+
+    def _device_op(self, op, other):
+        """self (op) other on the device, or NotImplemented when numpy's own rules are needed (type
+        promotion, general broadcasting, integer / complex operands)."""
+        kind = self._kind()
+        if kind is None:
+            return NotImplemented
+        real = np.dtype(np.float32) if kind in (1, 3) else np.dtype(np.float64)
+        if kind >= 2 and op == "rdiv":
+            return NotImplemented
+        if isinstance(other, (bool, np.bool_)):
+            return NotImplemented
+        if isinstance(other, (int, float, np.integer, np.floating)):
+            if isinstance(other, np.floating) and other.dtype.itemsize > real.itemsize:
+                return NotImplemented            # float32 map (op) np.float64 scalar promotes in numpy 2
+            out = devmap.empty(self.shape, self.dtype, self.wcs)
+            check(lib.ox_map_op(_OPS[op], C.c_void_p(self.ptr), None, C.c_double(float(other)), self.size, 0, kind, C.c_void_p(out._ptr)))
+            return out
+        if isinstance(other, devmap):
+            b = other
+        elif isinstance(other, np.ndarray):
+            if other.dtype != real or other.ndim == 0:
+                return NotImplemented
+            b = None
+        else:
+            return NotImplemented
+        oshape = tuple(other.shape)
+        if np.dtype(other.dtype) != real:
+            return NotImplemented
+        # the operand must be the trailing axes of self (equal shapes, or a (Ny,Nx) taper against (ncomp,Ny,Nx))
+        if len(oshape) > self.ndim or oshape != self.shape[self.ndim - len(oshape):] or not oshape:
+            return NotImplemented
+        if b is None:
+            b = devmap.from_host(other)
+        out = devmap.empty(self.shape, self.dtype, self.wcs if self.wcs is not None else getattr(other, "wcs", None))
+        check(lib.ox_map_op(_OPS[op], C.c_void_p(self.ptr), C.c_void_p(b.ptr), C.c_double(0.0), self.size, b.size, kind,
+                            C.c_void_p(out._ptr)))
+        return out
+
+    def _binop(self, op, other, ufunc, reflected):
+        r = self._device_op(_REFLECT[op] if reflected else op, other)
+        if r is not NotImplemented:
+            return r
+        o = other.host() if isinstance(other, devmap) else other
+        return ufunc(o, self.host()) if reflected else ufunc(self.host(), o)
+
+    def __mul__(self, o): return self._binop("mul", o, np.multiply, False)
+    def __rmul__(self, o): return self._binop("mul", o, np.multiply, True)
+    def __add__(self, o): return self._binop("add", o, np.add, False)
+    def __radd__(self, o): return self._binop("add", o, np.add, True)
+    def __sub__(self, o): return self._binop("sub", o, np.subtract, False)
+    def __rsub__(self, o): return self._binop("sub", o, np.subtract, True)
+    def __truediv__(self, o): return self._binop("div", o, np.true_divide, False)
+    def __rtruediv__(self, o): return self._binop("div", o, np.true_divide, True)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        # host_array * devmap etc. arrive here; the four arithmetic ufuncs stay on the device, the rest is numpy's
+        if method == "__call__" and not kwargs and len(inputs) == 2 and ufunc in _UFUNC_OPS:
+            a, b = inputs
+            op = _UFUNC_OPS[ufunc]
+            if isinstance(a, devmap):
+                r = a._device_op(op, b)
+            else:
+                r = b._device_op(_REFLECT[op], a)
+            if r is not NotImplemented:
+                return r
+        if "out" in kwargs:
+            kwargs["out"] = tuple(o.host() if isinstance(o, devmap) else o for o in kwargs["out"])
+        args = [x.host() if isinstance(x, devmap) else x for x in inputs]
+        return getattr(ufunc, method)(*args, **kwargs)
+
+
+def _host_fallback(name):
+    def f(self, *args):
+        args = [a.host() if isinstance(a, devmap) else a for a in args]
+        return getattr(self.host(), name)(*args)
+    f.__name__ = name
+    return f
+
+
+for _n in ("__neg__", "__pos__", "__abs__", "__pow__", "__rpow__", "__floordiv__", "__rfloordiv__", "__mod__", "__rmod__",
+           "__matmul__", "__rmatmul__", "__lt__", "__le__", "__gt__", "__ge__", "__eq__", "__ne__", "__and__", "__or__",
+           "__xor__", "__invert__", "__bool__", "__float__", "__int__", "__complex__", "__contains__"):
+    setattr(devmap, _n, _host_fallback(_n))
+devmap.__hash__ = None
+
+
+def to_device(x, dtype=None, wcs=None):
+    """devmap of x: x itself when it already is one of that dtype, else an upload (both copies kept)."""
+    if isinstance(x, devmap) and (dtype is None or x.dtype == np.dtype(dtype)):
+        return x
+    a = np.asarray(x) if dtype is None else np.asarray(x, dtype=dtype)
+    return devmap.from_host(a, getattr(x, "wcs", None) if wcs is None else wcs)
+
+
+def result_map(shape, dtype, wcs):
+    """(array-or-devmap, void* argument, OX_HOST | OX_DEVICE) for an output of a reference-signature call."""
+    if DEVICE_RESIDENT:
+        d = devmap.empty(shape, dtype, wcs)
+        return d, C.c_void_p(d._ptr), _capi.OX_DEVICE
+    a = np.empty(shape, dtype=dtype)
+    return ndmap(a, wcs), ptr(a), _capi.OX_HOST
 
 
 def enmap(arr, wcs=None):

@@ -1,0 +1,25 @@
+#!/bin/bash
+# round-2 GPU call 4: TMA row pass with the static schedule + shared-memory tables
+mkdir -p gpurun_out
+( time timeout 600 python -m pytest tests/test_gpu_sim_power.py -m gpu -x -q -k "tma_row or fused_pipeline or fused_and_cufft" ) > gpurun_out/r02_tests4.log 2>&1
+tail -6 gpurun_out/r02_tests4.log
+for v in "tma 1" "legacy 1" "tma 0"; do
+  set -- $v
+  ORPHX_KB=$1 ORPHX_WINDOW_SEPARABLE=$2 timeout 300 python bench.py --steps 32 --warmup 3 --configs none --no-extras --cpu-sample 0 --no-e2e > gpurun_out/r02_bench4_$1_$2.json 2> gpurun_out/r02_bench4_$1_$2.err
+  python - <<PY
+import json
+try:
+    e=json.load(open('gpurun_out/r02_bench4_$1_$2.json')); print('$1 sepwin=$2', round(e['value']), {k:round(v['ms_per_launch'],3) for k,v in e['stages'].items()})
+except Exception as ex: print('$1 $2 failed', ex)
+PY
+done
+timeout 600 python bench.py --steps 8 --warmup 3 --configs 2,3 --no-extras --cpu-sample 0 --no-e2e > gpurun_out/r02_bench4_cfg.json 2> gpurun_out/r02_bench4_cfg.err
+python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/r02_bench4_cfg.json'))['configs']
+    for k,e in d.items(): print(k, round(e['value'],1), {s:round(v['ms_per_launch'],3) for s,v in e.get('stages',{}).items()})
+except Exception as ex: print('cfg failed', ex)
+PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_row_tma --launch-skip 3 --launch-count 1 -o gpurun_out/prof_r02e -f python bench.py --steps 1 --warmup 3 --no-e2e --cpu-sample 0 --batch 64 --no-extras --configs none > gpurun_out/ncu_r02e.log 2>&1
+ls -la gpurun_out | tail -3
