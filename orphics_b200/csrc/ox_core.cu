@@ -350,6 +350,7 @@ int ox_free_pooled(void *dptr) {
   return OX_OK;
 }
 
+}  // extern "C"
 namespace {
 // out[i] = a[i] (op) b[i % nb]  (or the scalar when b == null); complex a / out with a real b
 template <typename TA, typename TB>
@@ -381,6 +382,7 @@ __global__ void map_op_kernel(int op, const TA *__restrict__ a, const TB *__rest
   }
 }
 }  // namespace
+extern "C" {
 
 // Elementwise arithmetic on device-resident maps (what `emap * taper`, `p2d / w2`, `map + noise` of the
 // reference's call sequences do in numpy; maps.py:1351, lensing.py:519).  kind: 0 f64, 1 f32 (a, b, out real),

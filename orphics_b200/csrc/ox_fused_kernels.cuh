@@ -355,6 +355,7 @@ struct RowCfg {
 
 }  // namespace oxk
 #include "ox_row_tma.cuh"
+#include "ox_row_w32.cuh"
 namespace oxk {
 
 template <typename T, int MX, int MODE>
@@ -364,6 +365,8 @@ int launch_row_mode(RowArgs<T> &a, long long nplanes) {
   {
     // Blackwell path: persistent CTAs fed by the TMA unit (ox_row_tma.cuh); ORPHX_KB=legacy keeps the kernel below
     bool launched = false;
+    OX_TRY((launch_row_w32<T, MX, MODE>(a, nplanes, &launched)));   // nx = 2048: one warp per row, radix 32
+    if (launched) return OX_OK;
     OX_TRY((launch_row_tma<T, MX, MODE>(a, nplanes, &launched)));
     if (launched) return OX_OK;
   }

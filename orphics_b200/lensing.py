@@ -15,7 +15,7 @@ import numpy as np
 from . import _capi
 from ._capi import lib, check, ptr, OX_HOST
 from . import enmap as _enmap
-from .enmap import Geometry, ndmap
+from .enmap import Geometry, ndmap, devmap
 
 #: bound on max|kappa - kappa_ref| / max|kappa_ref| of the float32 estimator against the float64 reference chain
 #: on the same (float32-representable) inputs: north_star's 1e-5.  Measured on B200: 7e-7 (TT) / 8e-7 (EB) at 512^2
@@ -186,19 +186,32 @@ class qest(object):
         h, _ = self._plans[XY]
         g = self.geometry.shape
         rdt, cdt = _capi.np_dtype(self.dtype), _capi.np_cdtype(self.dtype)
-        idt = cdt if alreadyFTed else rdt
-        x = np.ascontiguousarray(X, dtype=idt).reshape((-1,) + g)
-        y = None if Y is None else np.ascontiguousarray(Y, dtype=idt).reshape((-1,) + g)
-        nb = x.shape[0]
+        idt = np.dtype(cdt if alreadyFTed else rdt)
+        npix = g[0] * g[1]
+        size = int(np.prod(np.shape(X), dtype=np.int64))
+        nb = size // npix
+        if nb * npix != size or tuple(np.shape(X)[-2:]) != tuple(g):
+            raise ValueError(f"input of shape {np.shape(X)} is not a stack of {g} maps")
+        if Y is not None and np.shape(Y) != np.shape(X):
+            raise ValueError("the X and Y legs must have one shape")
         if nb > self.max_batch:
             raise ValueError(f"{nb} realisations but max_batch={self.max_batch}")
+        dev = isinstance(X, devmap) and X.dtype == idt and (Y is None or (isinstance(Y, devmap) and Y.dtype == idt))
+        if dev:     # device-resident inputs (FourierCalc.power2d's k-maps, MapGen's maps) are consumed in HBM
+            xp, yp, loc = C.c_void_p(X.ptr), (None if Y is None else C.c_void_p(Y.ptr)), _capi.OX_DEVICE
+        else:
+            x = np.ascontiguousarray(np.asarray(X), dtype=idt)
+            y = None if Y is None else np.ascontiguousarray(np.asarray(Y), dtype=idt)
+            xp, yp, loc = ptr(x), ptr(y), OX_HOST
         odt = cdt if returnFt else rdt
         if out is None:
-            out = np.empty((nb,) + g, dtype=odt)
-        elif out.dtype != odt or out.size != nb * g[0] * g[1] or not out.flags["C_CONTIGUOUS"]:
-            raise ValueError("out must be a C-contiguous array of the result's dtype and size")
-        check(lib.ox_qe_reconstruct(h, ptr(x), ptr(y), OX_HOST, nb, int(bool(alreadyFTed)), int(bool(returnFt)),
-                                    int(bool(accumulate)), ptr(out), OX_HOST))
+            out, optr, oloc = _enmap.result_map((nb,) + g, odt, self.wcs)
+        else:
+            if out.dtype != odt or out.size != nb * npix or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a C-contiguous array of the result's dtype and size")
+            optr, oloc = ptr(out), OX_HOST
+        check(lib.ox_qe_reconstruct(h, xp, yp, loc, nb, int(bool(alreadyFTed)), int(bool(returnFt)),
+                                    int(bool(accumulate)), optr, oloc))
         return out
 
     def kappa_from_map(self, XY, T2DData, E2DData=None, B2DData=None, T2DDataY=None, E2DDataY=None, B2DDataY=None,
@@ -212,7 +225,7 @@ class qest(object):
         if X is None or Y is None:
             raise ValueError(f"{XY} needs the {Xl} and {Yl} maps")
         out = self._run(XY, X, None if (Y is X) else Y, alreadyFTed, returnFt, accumulate_meanfield)[0]
-        return ndmap(out, self.wcs)
+        return out if isinstance(out, devmap) else ndmap(out, self.wcs)
 
     reconstruct = kappa_from_map
 

@@ -13,7 +13,16 @@ import numpy as np
 
 from . import _capi, enmap
 from ._capi import lib, check, ptr, OX_HOST, OX_DEVICE
-from .enmap import Geometry, ndmap
+from .enmap import Geometry, ndmap, devmap, result_map
+
+
+def _dev_in(x, dtype):
+    """(void* argument, OX_HOST | OX_DEVICE, keep-alive) of an input array: a devmap of the plan's dtype is consumed
+    in HBM, anything else goes through a C-contiguous host array of that dtype."""
+    if isinstance(x, devmap) and x.dtype == np.dtype(dtype):
+        return C.c_void_p(x.ptr), OX_DEVICE, x
+    a = np.ascontiguousarray(np.asarray(x), dtype=dtype)
+    return ptr(a), OX_HOST, a
 
 
 # --------------------------------------------------------------------------- geometry
@@ -211,11 +220,8 @@ class MapGen(object):
                 for i, s in enumerate(seeds):
                     self._numpy_noise(s, noise[i])
         rdt, cdt = _capi.np_dtype(self.dtype), _capi.np_cdtype(self.dtype)
-        if flags & _capi.FLAG_HARM:
-            out = np.empty((nsim, self.ncomp) + self.geometry.shape, dtype=cdt)
-        else:
-            out = np.empty((nsim, self.ncomp) + self.geometry.shape, dtype=rdt)
-        check(lib.ox_sim_generate(self.handle, ptr(seeds64), nsim, mode, ptr(noise), OX_HOST, flags, ptr(out), OX_HOST))
+        out, optr, oloc = result_map((nsim, self.ncomp) + self.geometry.shape, cdt if flags & _capi.FLAG_HARM else rdt, self.wcs)
+        check(lib.ox_sim_generate(self.handle, ptr(seeds64), nsim, mode, ptr(noise), OX_HOST, flags, optr, oloc))
         return out
 
     def _flags(self, scalar, iau, harm):
@@ -237,14 +243,14 @@ class MapGen(object):
         out = self._generate([seed], self._flags(scalar, iau, harm))[0]
         if len(self.shape) == 2:
             out = out[0]
-        return ndmap(out, self.wcs)
+        return out if isinstance(out, devmap) else ndmap(out, self.wcs)
 
     def get_maps(self, seeds, scalar=False, iau=False, harm=False, noise=None):
         """Batched get_map: (nsim,[ncomp,]Ny,Nx)."""
         out = self._generate(list(seeds), self._flags(scalar, iau, harm), noise_mode=noise)
         if len(self.shape) == 2:
-            out = out[:, 0]
-        return ndmap(out, self.wcs)
+            out = out.reshape((out.shape[0],) + out.shape[2:])
+        return out if isinstance(out, devmap) else ndmap(out, self.wcs)
 
     def __del__(self):
         try:
@@ -293,13 +299,20 @@ class FourierCalc(object):
         return h
 
     def _as_stack(self, emap):
-        a = np.asarray(emap)
-        if np.iscomplexobj(a):
+        """(void* argument, location, ncomp, keep-alive) of a real map (ncomp,Ny,Nx) or (Ny,Nx)."""
+        shp, dt = tuple(np.shape(emap)), getattr(emap, "dtype", None)
+        if dt is None:
+            emap = np.asarray(emap)
+            shp, dt = emap.shape, emap.dtype
+        if np.issubdtype(dt, np.complexfloating):
             raise NotImplementedError("FourierCalc transforms real maps; complex input is outside the accelerated path")
-        if a.shape[-2:] != self.geometry.shape:
-            raise ValueError(f"map shape {a.shape} does not match geometry {self.geometry.shape}")
-        nc = a.shape[-3] if a.ndim > 2 else 1
-        return np.ascontiguousarray(a, dtype=_capi.np_dtype(self.dtype)).reshape((1, nc) + self.geometry.shape), nc
+        if shp[-2:] != self.geometry.shape:
+            raise ValueError(f"map shape {shp} does not match geometry {self.geometry.shape}")
+        nc = shp[-3] if len(shp) > 2 else 1
+        if int(np.prod(shp, dtype=np.int64)) != nc * self.geometry.npix:
+            raise ValueError(f"map shape {shp}: expected ([ncomp,] Ny, Nx)")
+        a, loc, keep = _dev_in(emap, _capi.np_dtype(self.dtype))
+        return a, loc, nc, keep
 
     def _flags(self, rot=True, pixel_units=False, skip_cross=False, normalize=False):
         f = 0
@@ -319,22 +332,29 @@ class FourierCalc(object):
         """2-D FFT of the map(s) with the QU->EB rotation (maps.py:1609-1617). nthread is ignored."""
         if normalize not in (True, False):
             raise NotImplementedError("normalize='phys' is outside the accelerated path")
-        stack, nc = self._as_stack(emap)
-        out = np.empty(stack.shape, dtype=_capi.np_cdtype(self.dtype))
+        a, loc, nc, _keep = self._as_stack(emap)
+        out, optr, oloc = result_map(np.shape(emap), _capi.np_cdtype(self.dtype), self.wcs)
         flags = self._flags(rot=rot and nc == 3, normalize=bool(normalize))
-        check(lib.ox_power_fft(self._plan(nc), ptr(stack), OX_HOST, 1, flags, ptr(out), OX_HOST))
-        return ndmap(out.reshape(np.shape(emap)), self.wcs)
+        check(lib.ox_power_fft(self._plan(nc), a, loc, 1, flags, optr, oloc))
+        return out
 
     def f2power(self, kmap1, kmap2, pixel_units=False):
         """Re(conj(k1) k2) * normfact for already transformed maps (maps.py:1620-1624)."""
         cdt = _capi.np_cdtype(self.dtype)
-        k1 = np.ascontiguousarray(kmap1, dtype=cdt)
-        k2 = k1 if kmap2 is kmap1 else np.ascontiguousarray(kmap2, dtype=cdt)
-        if k1.shape != k2.shape:
+        if np.shape(kmap1) != np.shape(kmap2):
             raise ValueError("kmap shapes differ")
-        out = np.empty(k1.shape, dtype=_capi.np_dtype(self.dtype))
-        check(lib.ox_power_f2power(self._plan(1), ptr(k1), ptr(k2), OX_HOST, k1.size, self._flags(rot=False, pixel_units=pixel_units), ptr(out), OX_HOST))
-        return out
+        dev = isinstance(kmap1, devmap) and isinstance(kmap2, devmap) and kmap1.dtype == kmap2.dtype == np.dtype(cdt)
+        if dev:
+            a1, a2, loc = C.c_void_p(kmap1.ptr), C.c_void_p(kmap2.ptr), OX_DEVICE
+        else:      # (the two k-maps share one location argument: mixed inputs go through the host)
+            k1 = np.ascontiguousarray(np.asarray(kmap1), dtype=cdt)
+            k2 = k1 if kmap2 is kmap1 else np.ascontiguousarray(np.asarray(kmap2), dtype=cdt)
+            a1, a2, loc = ptr(k1), ptr(k2), OX_HOST
+        shp = np.shape(kmap1)
+        out, optr, oloc = result_map(shp, _capi.np_dtype(self.dtype), getattr(kmap1, "wcs", None))
+        check(lib.ox_power_f2power(self._plan(1), a1, a2, loc, int(np.prod(shp, dtype=np.int64)),
+                                   self._flags(rot=False, pixel_units=pixel_units), optr, oloc))
+        return out if isinstance(out, devmap) else np.asarray(out)
 
     def f1power(self, map1, kmap2, pixel_units=False, nthread=0):
         """maps.py:1626-1630."""
@@ -344,11 +364,12 @@ class FourierCalc(object):
     def ifft(self, kmap):
         """Backward c2c / Npix (maps.py:1632-1633)."""
         cdt = _capi.np_cdtype(self.dtype)
-        k = np.ascontiguousarray(kmap, dtype=cdt)
-        nc = k.shape[-3] if k.ndim > 2 else 1
-        out = np.empty(k.shape, dtype=cdt)
-        check(lib.ox_power_ifft(self._plan(nc), ptr(k), OX_HOST, 1, ptr(out), OX_HOST))
-        return ndmap(out, self.wcs)
+        shp = np.shape(kmap)
+        nc = shp[-3] if len(shp) > 2 else 1
+        a, loc, _keep = _dev_in(kmap, cdt)
+        out, optr, oloc = result_map(shp, cdt, self.wcs)
+        check(lib.ox_power_ifft(self._plan(nc), a, loc, 1, optr, oloc))
+        return out
 
     def fft(self, emap):
         """Raw forward FFT, no rotation (maps.py:1635-1636)."""
@@ -379,43 +400,63 @@ class FourierCalc(object):
                 return retpow, lteb1, lteb2
             if ndim > 2:
                 lteb1, lteb2 = lteb1[0], lteb2[0]
-            return ndmap(self.f2power(lteb1, lteb2, pixel_units), wcs), ndmap(lteb1, wcs), ndmap(lteb2, wcs)
-        s1, nc = self._as_stack(emap)
-        s2 = None
+            keep = lambda m: m if isinstance(m, devmap) else ndmap(m, wcs)
+            return keep(self.f2power(lteb1, lteb2, pixel_units)), keep(lteb1), keep(lteb2)
+        a1, loc1, nc, _k1 = self._as_stack(emap)
+        a2 = None
         if emap2 is not None:
-            s2, nc2 = self._as_stack(emap2)
-            assert s1.shape == s2.shape
+            a2, loc2, nc2, _k2 = self._as_stack(emap2)
+            assert np.shape(emap) == np.shape(emap2)
+            if loc2 != loc1:       # (the two maps share one location argument)
+                dt = _capi.np_dtype(self.dtype)
+                _k1, _k2 = np.ascontiguousarray(np.asarray(emap), dtype=dt), np.ascontiguousarray(np.asarray(emap2), dtype=dt)
+                a1, a2, loc1 = ptr(_k1), ptr(_k2), OX_HOST
         rdt, cdt = _capi.np_dtype(self.dtype), _capi.np_cdtype(self.dtype)
-        p2d = np.empty((nc, nc) + self.geometry.shape, dtype=rdt)
-        k1 = np.empty(s1.shape, dtype=cdt)
-        k2 = np.empty(s1.shape, dtype=cdt) if s2 is not None else None
+        multi = np.ndim(emap) > 2 and nc > 1
+        kshape = (nc,) + self.geometry.shape if np.ndim(emap) > 2 else self.geometry.shape
+        p2d, pptr, oloc = result_map((nc, nc) + self.geometry.shape if multi else self.geometry.shape, rdt, None if multi else wcs)
+        k1, k1ptr, _ = result_map(kshape, cdt, wcs)
+        k2, k2ptr = k1, None
+        if a2 is not None:
+            k2, k2ptr, _ = result_map(kshape, cdt, wcs)
         flags = self._flags(rot=rot and nc == 3, pixel_units=pixel_units, skip_cross=skip_cross)
-        check(lib.ox_power2d(self._plan(nc), ptr(s1), ptr(s2), OX_HOST, 1, flags, ptr(p2d), ptr(k1), ptr(k2), OX_HOST))
-        if k2 is None:
-            k2 = k1
-        if np.ndim(emap) > 2 and nc > 1:
-            ret = p2d if dtype is None else p2d.astype(dtype)
-            return ret, ndmap(k1[0], wcs), ndmap(k2[0], wcs)
-        return ndmap(p2d[0, 0], wcs), ndmap(k1[0, 0], wcs), ndmap(k2[0, 0], wcs)
+        check(lib.ox_power2d(self._plan(nc), a1, a2, loc1, 1, flags, pptr, k1ptr, k2ptr, oloc))
+        if multi:
+            # the reference returns a plain (ncomp,ncomp,Ny,Nx) array here (np.zeros, maps.py:1662)
+            if dtype is not None:
+                p2d = np.asarray(p2d).astype(dtype)
+            elif not isinstance(p2d, devmap):
+                p2d = np.asarray(p2d)
+            return p2d, k1, k2
+        if np.ndim(emap) > 2:
+            k1, k2 = k1[0], k2[0]
+        return p2d, k1, k2
 
     # ---- batched / fused additions
     def binned_power_batch(self, binner, maps, maps2=None, window=None, pixel_units=False, skip_cross=False, rot=True):
         """power2d + bin2D.bin for a stack (nbatch,[ncomp,]Ny,Nx) without materialising p2d;
         returns bandpowers (nbatch, nspec, nbins), nspec ordered (0,0),(0,1)..,(1,1),.. .
         ``binner`` must be a stats.bin2D built with geometry=."""
-        a = np.asarray(maps)
         nc = self.ncomp
         rdt = _capi.np_dtype(self.dtype)
-        s1 = np.ascontiguousarray(a, dtype=rdt).reshape((-1, nc) + self.geometry.shape)
-        nb = s1.shape[0]
-        s2 = None
+        size = int(np.prod(np.shape(maps), dtype=np.int64))
+        nb = size // (nc * self.geometry.npix)
+        if nb * nc * self.geometry.npix != size or np.shape(maps)[-2:] != self.geometry.shape:
+            raise ValueError(f"maps of shape {np.shape(maps)} are not a stack of ({nc},) + {self.geometry.shape} maps")
+        a1, loc, _k1 = _dev_in(maps, rdt)
+        a2 = None
         if maps2 is not None:
-            s2 = np.ascontiguousarray(maps2, dtype=rdt).reshape(s1.shape)
-        w = None if window is None else np.ascontiguousarray(window, dtype=rdt)
+            if np.shape(maps2) != np.shape(maps):
+                raise ValueError("maps2 must have the shape of maps")
+            a2, loc2, _k2 = _dev_in(maps2, rdt)
+            if loc2 != loc:
+                _k1, _k2 = np.ascontiguousarray(np.asarray(maps), dtype=rdt), np.ascontiguousarray(np.asarray(maps2), dtype=rdt)
+                a1, a2, loc = ptr(_k1), ptr(_k2), OX_HOST
+        wp, wloc, _kw = (None, OX_HOST, None) if window is None else _dev_in(window, rdt)
         ns = nc if (skip_cross and nc > 1) else nc * (nc + 1) // 2
         out = np.empty((nb, ns, binner.centers.size), dtype=np.float64)
         flags = self._flags(rot=rot and nc == 3, pixel_units=pixel_units, skip_cross=skip_cross)
-        check(lib.ox_power_bin(self._plan(nc, nb), binner.handle, ptr(s1), ptr(s2), OX_HOST, nb, flags, ptr(w), OX_HOST, ptr(out), OX_HOST))
+        check(lib.ox_power_bin(self._plan(nc, nb), binner.handle, a1, a2, loc, nb, flags, wp, wloc, ptr(out), OX_HOST))
         # bin2D's short-bincount quirk (stats.py:796-797): same length as binner.bin() returns
         return out[..., :binner.trimmed_nbins]
 
@@ -478,6 +519,9 @@ def get_taper(shape, wcs, taper_percent=12.0, pad_percent=3.0, weight=None):
     pad = int(pad_percent * min(Ny, Nx) / 100.)
     taper = cosine_window(Ny, Nx, lenApodY=apod, lenApodX=apod, padY=pad, padX=pad) * weight
     w2 = np.mean(taper ** 2.)
+    if enmap.DEVICE_RESIDENT:
+        # host and device copies: `imap * taper` with a device-resident imap stays on the device
+        return devmap.from_host(taper, wcs), w2
     return ndmap(taper, wcs), w2
 
 
@@ -602,12 +646,16 @@ def filter_map(imap, kfilter, fc=None):
     fc = FourierCalc(imap.shape, imap.wcs) if fc is None else fc
     if np.iscomplexobj(kfilter):
         raise NotImplementedError("filter_map: complex kfilter is outside the accelerated path")
-    stack, nc = fc._as_stack(imap)
-    kf = np.ascontiguousarray(np.broadcast_to(np.asarray(kfilter, dtype=np.float64), fc.geometry.shape))
-    out = np.empty(stack.shape, dtype=stack.dtype)
+    a, loc, nc, _keep = fc._as_stack(imap)
+    if isinstance(kfilter, devmap) and kfilter.dtype == np.float64 and kfilter.shape == fc.geometry.shape:
+        kp, kloc, _kk = C.c_void_p(kfilter.ptr), OX_DEVICE, kfilter
+    else:
+        _kk = np.ascontiguousarray(np.broadcast_to(np.asarray(kfilter, dtype=np.float64), fc.geometry.shape))
+        kp, kloc = ptr(_kk), OX_HOST
+    out, optr, oloc = result_map(np.shape(imap), _capi.np_dtype(fc.dtype), getattr(imap, "wcs", fc.wcs))
     # one device pass: r2c -> x 1/2[f(l)+f(-l)]/Npix -> c2r (ox_power_filter)
-    check(lib.ox_power_filter(fc._plan(nc), ptr(stack), OX_HOST, 1, ptr(kf), OX_HOST, ptr(out), OX_HOST))
-    return ndmap(out.reshape(np.shape(imap)), getattr(imap, "wcs", fc.wcs))
+    check(lib.ox_power_filter(fc._plan(nc), a, loc, 1, kp, kloc, optr, oloc))
+    return out
 
 
 # --------------------------------------------------------------------------- fused pipeline

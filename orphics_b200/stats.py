@@ -66,19 +66,26 @@ class bin2D(object):
         return self._digitized
 
     def _raw(self, data, weights, flags):
-        data = np.asarray(data)
+        from .enmap import devmap
+        if not isinstance(data, devmap):
+            data = np.asarray(data)
         # float32 data stay float32 on the device unless weights are given: the reference's weights are float64
         # (np.bincount promotes), so weighted sums are formed in float64
         dt = _capi.OX_F32 if (data.dtype == np.float32 and weights is None) else _capi.OX_F64
-        d = np.ascontiguousarray(data, dtype=_capi.np_dtype(dt))
-        if d.size % self._n != 0:
-            raise ValueError(f"data size {d.size} is not a multiple of the binner's {self._n} pixels")
-        nmaps = d.size // self._n
+        if data.size % self._n != 0:
+            raise ValueError(f"data size {data.size} is not a multiple of the binner's {self._n} pixels")
+        nmaps = data.size // self._n
+        sums = np.empty((nmaps, self.nslots), dtype=np.float64)
+        cnts = np.empty((nmaps, self.nslots), dtype=np.float64)
+        if isinstance(data, devmap) and weights is None and data.dtype == _capi.np_dtype(dt):
+            # a device-resident map (FourierCalc.power2d's result) is binned where it is
+            check(lib.ox_binner_bin(self.handle, C.c_void_p(data.ptr), dt, _capi.OX_DEVICE, nmaps, None, flags, ptr(sums), ptr(cnts),
+                                    _capi.OX_HOST))
+            return sums, cnts
+        d = np.ascontiguousarray(np.asarray(data), dtype=_capi.np_dtype(dt))
         w = None
         if weights is not None:
             w = np.ascontiguousarray(np.broadcast_to(np.asarray(weights), np.shape(self.modrmap)), dtype=d.dtype)
-        sums = np.empty((nmaps, self.nslots), dtype=np.float64)
-        cnts = np.empty((nmaps, self.nslots), dtype=np.float64)
         check(lib.ox_binner_bin(self.handle, ptr(d), dt, _capi.OX_HOST, nmaps, ptr(w), flags, ptr(sums), ptr(cnts), _capi.OX_HOST))
         return sums, cnts
 
@@ -90,7 +97,9 @@ class bin2D(object):
         return arr[:length][1:-1]
 
     def bin(self, data2d, weights=None, err=False, get_count=False, mask_nan=False):
-        data2d = np.asarray(data2d)
+        from .enmap import devmap
+        if not isinstance(data2d, devmap) or err or weights is not None:
+            data2d = np.asarray(data2d)
         if data2d.size != self._n:
             raise ValueError("data2d does not match the binner's modrmap size; use bin_batch for stacks")
         if weights is None:
@@ -126,7 +135,9 @@ class bin2D(object):
 
     def bin_batch(self, data, mask_nan=False):
         """Bin a stack (..., Ny, Nx) in one device pass; returns (centers, res[..., nbins])."""
-        data = np.asarray(data)
+        from .enmap import devmap
+        if not isinstance(data, devmap):
+            data = np.asarray(data)
         lead = data.shape[:-np.ndim(self.modrmap)] if np.ndim(self.modrmap) else data.shape[:-1]
         sums, cnts = self._raw(data, None, _capi.FLAG_MASK_NAN if mask_nan else 0)
         out = []

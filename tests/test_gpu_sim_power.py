@@ -400,8 +400,8 @@ def test_multi_pow_on_device_matches_eigpow(theory):
 
 @pytest.mark.parametrize("pol", [False, True])
 def test_tma_row_pass_matches_the_legacy_row_pass_and_the_oracle(pol, theory, monkeypatch):
-    """The persistent TMA row kernel (ox_row_tma.cuh: cp.async.bulk.tensor tiles, three slots, two groups per CTA)
-    runs the same butterflies as the one-tile-per-CTA kernel (the compiler contracts multiply-adds differently in
+    """The persistent TMA row kernels (ox_row_tma.cuh: cp.async.bulk.tensor tiles, three slots, two groups per CTA;
+    ox_row_w32.cuh: the same with one warp per row and two radix-32 stages) agree with the one-tile-per-CTA kernel (the compiler contracts multiply-adds differently in
     the two instantiations, so agreement is to rounding, 1e-13, not bit for bit), on a 512 x 2048 patch (nx/2 = 1024:
     the 2048^2 configuration's row length), with the separable-window fast path and with the general 2-D window --
     and matches the oracle on numpy seeds."""
@@ -416,7 +416,8 @@ def test_tma_row_pass_matches_the_legacy_row_pass_and_the_oracle(pol, theory, mo
     taper = np.asarray(maps.get_taper(shape, wcs)[0])
     nsim = 5                                                     # 5 planes x 128 row tiles: odd tile counts per CTA
     out = {}
-    for kb in ("legacy", "tma", "tma_general_window"):
+    variants = ("tma", "tma_general_window", "w32", "w32_general_window")
+    for kb in ("legacy",) + variants:
         monkeypatch.setenv("ORPHX_KB", kb.split("_")[0])
         monkeypatch.setenv("ORPHX_WINDOW_SEPARABLE", "0" if "general" in kb else "1")
         mg = maps.MapGen(shape, wcs, ps, noise="numpy", max_batch=nsim)
@@ -426,12 +427,12 @@ def test_tma_row_pass_matches_the_legacy_row_pass_and_the_oracle(pol, theory, mo
         assert pipe.path == "fused"
         bp = pipe.run(range(40, 40 + nsim), keep_maps=True)
         out[kb] = (bp, pipe.last_maps(nsim))
-    for kb in ("tma", "tma_general_window"):
+    for kb in variants:
         assert np.array_equal(np.isnan(out[kb][0]), np.isnan(out["legacy"][0]))
         fin = np.isfinite(out["legacy"][0])
         assert np.max(np.abs(out[kb][0] - out["legacy"][0])[fin] / np.abs(out["legacy"][0])[fin].max()) < 1e-13
         assert relerr(out[kb][1], out["legacy"][1]) < 1e-13
-    bp, stored = out["tma"]
+    bp, stored = out["w32"]       # (the default at nx = 2048: one warp per row, two radix-32 stages, ox_row_w32.cuh)
     pairs = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)] if pol else [(0, 0)]
     auto = {0: 0, 1: 3, 2: 5}
     for i in (0, nsim - 1):
