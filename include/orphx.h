@@ -63,6 +63,7 @@ typedef struct ox_powerplan ox_powerplan;
 typedef struct ox_pipeline ox_pipeline;
 typedef struct ox_qeplan ox_qeplan;
 typedef struct ox_comm ox_comm;
+typedef struct ox_lensplan ox_lensplan;
 
 /* ---- runtime ------------------------------------------------------------- */
 int ox_abi_version(void);
@@ -260,6 +261,25 @@ int ox_ilc(const void *kmaps, const double *cinv, const double *response_a, cons
  * the symmetric n x n matrices mat[n][n][npix] (float64, n <= 4) through a Jacobi eigen-decomposition; for a
  * non-integer or negative exponent, eigenvalues that are negative or below 1e-13 of the largest are zeroed. */
 int ox_multi_pow(const double *mat, int n, long long npix, double exponent, int where, double *out, int out_where);
+
+/* ---- lensing of flat-sky maps (the step before the estimator in FlatLensingSims.get_sim, lensing.py:499-521).
+ * A plan belongs to a geometry; py, px = pixel height and width in radians (enmap.pixshape, lensing.py:420);
+ * max_planes >= the largest taylor_order used (>= 2).  float64 throughout, maps [nmaps][ny][nx].
+ *  ox_lens_kappa_to_phi  lensing.kappa_to_phi (lensing.py:651-665): phi = Re ifft(2 fft(kappa) / (L (L+1))), 0 for L < 2.
+ *  ox_lens_set_phi       deflection alpha = Re ifft(i l fft(phi)) and its split into nearest pixel + remainder
+ *                        (flat_taylens, lensing.py:411-427), kept in the plan.
+ *  ox_lens_alpha         that deflection, [2][ny][nx] = (alphaY, alphaX) in radians (alpha_from_kappa's grad phi, lensing.py:443-449).
+ *  ox_lens_taylens       flat_taylens (lensing.py:395-440): imap[(iy+aY0)%Ny, (ix+aX0)%Nx] + the Taylor series in the
+ *                        remainder up to taylor_order - 1, every derivative a half-plane inverse transform.
+ *  ox_lens_displace      bicubic (Keys a = -1/2) interpolation at (iy + alphaY/py, ix + alphaX/px), periodic: the stand-in
+ *                        for pixell.lensing.displace_map (lensing.py:512; third party, spline of order lens_order). */
+int ox_lensplan_create(ox_geometry *g, double py, double px, int max_planes, ox_lensplan **out);
+int ox_lensplan_destroy(ox_lensplan *p);
+int ox_lens_kappa_to_phi(ox_lensplan *p, const double *kappa, int where, double *phi_out, int out_where);
+int ox_lens_set_phi(ox_lensplan *p, const double *phi, int where);
+int ox_lens_alpha(ox_lensplan *p, double *alpha_out, int out_where);
+int ox_lens_taylens(ox_lensplan *p, const double *imap, int where, int nmaps, int taylor_order, double *out, int out_where);
+int ox_lens_displace(ox_lensplan *p, const double *imap, int where, int nmaps, double *out, int out_where);
 
 /* ---- the exchange step: Statistics.allreduce (stats.py:1184-1232, mpi4py Allreduce(SUM)) as NCCL sum
  * all-reduces over NVLink, one process per GPU.  Rank 0 obtains the 128-byte NCCL unique id and the host

@@ -49,6 +49,42 @@ def flat_taylens(phi, imap, taylor_order=5):
     return enmap.ndmap(lensed, wcs)
 
 
+def grad_phi(phi):
+    """(d phi/dy, d phi/dx) by FFT, (2, Ny, Nx): the deflection flat_taylens forms at lensing.py:414-419 and
+    alpha_from_kappa's grad branch (lensing.py:443-449)."""
+    wcs = phi.wcs
+    f = lambda x: np.asarray(enmap.fft(enmap.ndmap(x, wcs), normalize="phys"))
+    invf = lambda x: np.asarray(enmap.ifft(enmap.ndmap(x, wcs), normalize="phys"))
+    kmap = f(phi)
+    ly_array, lx_array = np.asarray(enmap.lmap(phi.shape, wcs))
+    return np.stack([np.real(invf(1j * ly_array * kmap)), np.real(invf(1j * lx_array * kmap))])
+
+
+def displace_bicubic(imap, phi):
+    """NOT a reference restatement: CPU definition of the bicubic stand-in for pixell.lensing.displace_map
+    (lensing.py:512) -- Keys cubic convolution (a = -1/2), periodic, at (iy + alphaY/py, ix + alphaX/px)."""
+    a = np.asarray(imap, dtype=np.float64)
+    Ny, Nx = a.shape[-2:]
+    alphaY, alphaX = grad_phi(phi)
+    py, px = enmap.extent(phi.shape, phi.wcs) / np.array(phi.shape)
+    iy, ix = np.mgrid[0:Ny, 0:Nx]
+    fy, fx = iy + alphaY / py, ix + alphaX / px
+    by, bx = np.floor(fy), np.floor(fx)
+
+    def weights(t):
+        t2, t3 = t * t, t * t * t
+        return [-0.5 * t3 + t2 - 0.5 * t, 1.5 * t3 - 2.5 * t2 + 1.0, -1.5 * t3 + 2.0 * t2 + 0.5 * t, 0.5 * t3 - 0.5 * t2]
+    wy, wx = weights(fy - by), weights(fx - bx)
+    y0, x0 = by.astype(np.int64) - 1, bx.astype(np.int64) - 1
+    out = np.zeros(a.shape)
+    for jy in range(4):
+        r = 0.0
+        for jx in range(4):
+            r = r + wx[jx] * a[..., (y0 + jy) % Ny, (x0 + jx) % Nx]
+        out = out + wy[jy] * r
+    return enmap.ndmap(out, phi.wcs)
+
+
 class FlatLensingSims:
     """lensing.py:458-521 (T-only or IQU), lensing by flat_taylens."""
 

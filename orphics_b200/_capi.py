@@ -124,6 +124,13 @@ SIGNATURES = {
     "ox_split_lensing_combine": [_vp, _i, _i, _i, C.c_longlong, _d, _vp, _i],
     "ox_ilc": [_vp, _vp, _vp, _vp, _i, C.c_longlong, _i, _i, _vp, _i],
     "ox_multi_pow": [_vp, _i, C.c_longlong, _d, _i, _vp, _i],
+    "ox_lensplan_create": [_vp, _d, _d, _i, _pvp],
+    "ox_lensplan_destroy": [_vp],
+    "ox_lens_kappa_to_phi": [_vp, _vp, _i, _vp, _i],
+    "ox_lens_set_phi": [_vp, _vp, _i],
+    "ox_lens_alpha": [_vp, _vp, _i],
+    "ox_lens_taylens": [_vp, _vp, _i, _i, _i, _vp, _i],
+    "ox_lens_displace": [_vp, _vp, _i, _i, _vp, _i],
 }
 
 for _name, _args in SIGNATURES.items():

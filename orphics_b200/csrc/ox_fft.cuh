@@ -250,10 +250,17 @@ struct BlockFFT {
   // persistent kernel.  Needs every exponent below L/2 in units of 1/(2L): REM in {1, 4, 8}.
   struct SmemTwiddles {
     static constexpr bool OK = P::REM == 1 || P::REM == 4 || P::REM == 8;
+    // The table is stored split by parity -- tab[tpos(j)], tpos(j) = j/2 for even j, L/8 + 1 + j/2 for odd j -- so that
+    // the last stage's exponents (even, consecutive lanes 2 apart) are contiguous 16-byte elements, and the 16
+    // exponents of the first radix-16 twiddle stage (8 (L/1024) apart) have a compact copy tab16[k].
+    static constexpr int TLEN = L / 4 + 1;
+    static __host__ __device__ constexpr int tpos(int j) { return (j & 1) ? L / 8 + 1 + (j >> 1) : (j >> 1); }
     const T2 *tab;
+    const T2 *tab16;   // tab16[k] = exp(-2 pi i k / 256), k < 16 (used when N16 >= 2)
     int u;
     __device__ __forceinline__ T2 get(int i) const {
       // i is a compile-time constant after unrolling: i < N16-1 -> radix-16 stage i+1, else butterfly q of the last stage
+      if (P::N16 >= 2 && i == 0) return tab16[u & 15];
       int Ns = 16, idx = 0;
       bool found = false;
 #pragma unroll
@@ -270,7 +277,7 @@ struct BlockFFT {
         idx = 2 * (j & (Ns - 1)) * (L / (Ns * (P::REM > 1 ? P::REM : 1)));
       }
       const bool hi = idx > L / 4;
-      const T2 t = tab[hi ? L / 2 - idx : idx];
+      const T2 t = tab[tpos(hi ? L / 2 - idx : idx)];
       T2 r;
       r.x = hi ? -t.y : t.x;
       r.y = hi ? -t.x : t.y;

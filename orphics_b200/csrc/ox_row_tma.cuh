@@ -108,13 +108,19 @@ struct RowTmaStore {
   const T2 *win_row;      // global or null (general window)
   const double2 *swinx;   // shared memory or null: x profile of a separable window as pairs, times wy
   double wy;
+  unsigned flat;          // bit m: the profile is exactly 1 for every thread's m-th output (no load needed)
   __device__ __forceinline__ void operator()(int n, T2 z, int m) const {
     if (!OUT_H || map_row != nullptr) st_once(map_row + n, z);
     if (OUT_H) {
       if (swinx != nullptr) {
-        const double2 p = swinx[n];
-        z.x *= (T)(p.x * wy);   // the window value itself is formed in float64 and rounded once, as numpy forms it
-        z.y *= (T)(p.y * wy);
+        if (flat & (1u << m)) {
+          z.x *= (T)wy;
+          z.y *= (T)wy;
+        } else {
+          const double2 p = swinx[n];
+          z.x *= (T)(p.x * wy);   // the window value itself is formed in float64 and rounded once, as numpy forms it
+          z.y *= (T)(p.y * wy);
+        }
       } else if (win_row != nullptr) {
         T2 w1 = ldg2(win_row + n);
         z.x *= w1.x;
@@ -136,8 +142,9 @@ struct RowTmaCfg {
   static constexpr size_t SLOT = (((WORK > TILE ? WORK : TILE) + 511) / 512) * 512;  // (the swizzle pattern repeats every 512 B)
   static constexpr size_t WINX = 8 * (size_t)(2 * MX);                    // x profile of a separable window
   static constexpr size_t UTW = 16 * (size_t)(MX / 4 + 1);                // exp(-2 pi i k / Nx), k <= Nx/8
-  static constexpr size_t SMEM_C2R = 3 * SLOT + 64 + UTW + 1024;          // slots + mbarriers + twiddles (+ alignment slack)
-  static constexpr size_t SMEM_FULL = 3 * SLOT + 64 + UTW + WINX + 1024;
+  static constexpr size_t TW16 = 16 * 16;                                 // compact copy of the 16 second-stage twiddles
+  static constexpr size_t SMEM_C2R = 3 * SLOT + 64 + UTW + TW16 + 1024;   // slots + mbarriers (+ flags) + twiddles (+ alignment slack)
+  static constexpr size_t SMEM_FULL = 3 * SLOT + 64 + UTW + TW16 + WINX + 1024;
   static constexpr int BOXW = 256;                                        // columns per TMA box
   static_assert(MX % BOXW == 0, "MX must be a multiple of the TMA box width");
 };
@@ -176,7 +183,8 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
   };
 
   {
-    // slots aligned to 1024 B; [3 slots][3 mbarriers (64 B)][twiddles][x profile of the window]
+    // slots aligned to 1024 B; [3 slots][3 mbarriers + flat-block mask (64 B)][twiddles, split by parity][16 second-stage
+    // twiddles][x profile of the window]
     unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
     if (threadIdx.x == 0) {
       unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT);
@@ -187,11 +195,23 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
       issue(base, 2);
     }
     T2 *utw = reinterpret_cast<T2 *>(base + 3 * Cfg::SLOT + 64);
+    T2 *tw16 = reinterpret_cast<T2 *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW);
+    unsigned *flat = reinterpret_cast<unsigned *>(base + 3 * Cfg::SLOT + 32);
     const int tws_n = a.tw_len / NX;
-    for (int e = threadIdx.x; e <= MX / 4; e += Cfg::NTHREADS) utw[e] = a.tw[e * tws_n];
+    for (int e = threadIdx.x; e <= MX / 4; e += Cfg::NTHREADS) utw[FFT::SmemTwiddles::tpos(e)] = a.tw[e * tws_n];
+    if (threadIdx.x < 16) tw16[threadIdx.x] = a.tw[threadIdx.x * (NX / 256) * tws_n];
+    if (threadIdx.x == 0) *flat = 0u;
+    __syncthreads();
     if (OUT_H && a.win_x != nullptr) {
-      double *swx = reinterpret_cast<double *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW);
+      double *swx = reinterpret_cast<double *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW + Cfg::TW16);
       for (int e = threadIdx.x; e < NX; e += Cfg::NTHREADS) swx[e] = a.win_x[e];
+      // bit m of the mask: the x profile is exactly 1 on columns [2 NT m, 2 NT (m+1)) -- the m-th last-stage outputs of
+      // every thread; there z * fl(1 * wy) = z * wy needs no profile load (70% of a cosine taper's columns)
+      if (threadIdx.x < 16) {
+        bool one = true;
+        for (int c = 0; c < 2 * NT; c++) one = one && (a.win_x[threadIdx.x * 2 * NT + c] == 1.0);
+        if (one) atomicOr(flat, 1u << threadIdx.x);
+      }
     }
     __syncthreads();
   }
@@ -218,6 +238,7 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     typename std::conditional<STW, typename FFT::SmemTwiddles, typename FFT::Twiddles>::type tws;
     if constexpr (STW) {
       tws.tab = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64);
+      tws.tab16 = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW);
       tws.u = u;
     } else {
       tws.init(a.tw, a.tw_len / MX, u);
@@ -234,15 +255,17 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
       wst.win_row = nullptr;
       wst.swinx = nullptr;
       wst.wy = 0.0;
+      wst.flat = 0u;
       if (OUT_H) {
         if (a.win_x != nullptr) {
-          wst.swinx = reinterpret_cast<const double2 *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW);
+          wst.swinx = reinterpret_cast<const double2 *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW + Cfg::TW16);
           wst.wy = a.win_y[iy0 + f];
+          wst.flat = *reinterpret_cast<const unsigned *>(base + 3 * Cfg::SLOT + 32);
         } else if (a.window != nullptr) {
           wst.win_row = reinterpret_cast<const T2 *>(a.window + (plane / a.group) * a.win_group_stride) + rowoff;
         }
       }
-      T2 wu = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64)[u];   // (u < MX/16: inside the table)
+      T2 wu = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64)[FFT::SmemTwiddles::tpos(u)];   // (u < MX/16: inside the table)
       wu.y = -wu.y;  // e^{+2 pi i u/Nx}
       mbar_wait(reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot, (unsigned)((i / 3) & 1));  // the tile has landed
       PackLoadTile<T2, MX, R> ld{s, f, wu};
@@ -266,7 +289,7 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
         const T2 *zr = s + r * PS;
         const T2 zk = zr[pad(k)], zm = zr[pad(k == 0 ? 0 : MX - k)];
         const bool hi = k > MX / 4;
-        const T2 wj = utw[hi ? MX / 2 - k : k];
+        const T2 wj = utw[FFT::SmemTwiddles::tpos(hi ? MX / 2 - k : k)];
         T2 w;
         w.x = hi ? -wj.y : wj.x;
         w.y = hi ? -wj.x : wj.y;

@@ -263,10 +263,13 @@ fused_row_w32_kernel(RowArgs<double> a, const __grid_constant__ CUtensorMap tmap
   }
 }
 
-// which persistent row pass at nx = 2048: ORPHX_KB = w32 (default) | tma (16 values per thread) | legacy
+// ORPHX_KB=w32 selects this kernel (an experiment kept for the record: it halves the shared-memory traffic -- L1 data
+// pipe 43% busy against 80% -- but with 254 registers only 8 warps fit an SM, and it measures 1.87 ms per 64 maps
+// against 1.58 ms for the 16-values-per-thread kernel, 2.65 against 2.10 with a general 2-D window;
+// profiles/r02_variants.txt)
 inline bool row_w32_enabled() {
   const char *e = getenv("ORPHX_KB");
-  return !(e && (!strcmp(e, "legacy") || !strcmp(e, "tma")));
+  return e && !strcmp(e, "w32");
 }
 
 template <typename T, int MX, int MODE>

@@ -376,45 +376,122 @@ class _C2C(object):
             pass
 
 
+class _LensPlan(object):
+    """Device state of the lensing callers for one geometry (ox_lensplan_*): transforms, the deflection field of the
+    current potential and its Taylens split."""
+
+    _cache = {}
+
+    def __init__(self, geometry, wcs, max_planes=8):
+        self.geometry = geometry
+        ext = _enmap.extent(geometry.shape, wcs, method=geometry.method)
+        self.py, self.px = ext[0] / geometry.shape[0], ext[1] / geometry.shape[1]     # enmap.pixshape (lensing.py:420)
+        self.max_planes = int(max_planes)
+        self.handle = C.c_void_p()
+        check(lib.ox_lensplan_create(geometry.handle, C.c_double(self.py), C.c_double(self.px), self.max_planes, C.byref(self.handle)))
+
+    @classmethod
+    def get(cls, shape, wcs, max_planes=8):
+        g = Geometry.get(shape, wcs)
+        key = (id(g), int(max_planes))
+        if key not in cls._cache:
+            cls._cache[key] = cls(g, wcs, max_planes)
+        return cls._cache[key]
+
+    def __del__(self):
+        try:
+            lib.ox_lensplan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _f64_in(x):
+    """(void* argument, location, keep-alive) of a float64 map for the lensing calls."""
+    if isinstance(x, devmap) and x.dtype == np.float64:
+        return C.c_void_p(x.ptr), _capi.OX_DEVICE, x
+    a = np.ascontiguousarray(np.asarray(x), dtype=np.float64)
+    return ptr(a), OX_HOST, a
+
+
 def kappa_to_phi(kappa, modlmap, return_fphi=False, _fft=None):
-    """lensing.py:651-657.  The reference transforms with enmap.fft/ifft(normalize='phys'): forward = raw FFT x
-    (pixsize/Npix)^1/2, backward = raw backward FFT / (pixsize Npix)^1/2.  The factors cancel in phi, but the
-    returned fphi carries the forward one."""
-    g = Geometry.get(kappa.shape, kappa.wcs)
+    """lensing.py:651-657: phi = Re ifft(2 fft(kappa) / (L (L+1))), on the device (ox_lens_kappa_to_phi).  The
+    reference transforms with enmap.fft/ifft(normalize='phys'): forward = raw FFT x (pixsize/Npix)^1/2, backward =
+    raw backward FFT / (pixsize Npix)^1/2.  The factors cancel in phi; the returned fphi carries the forward one.
+    ``modlmap`` must be the geometry's (as the reference passes kappa.modlmap()); any other array takes the generic
+    route through full-plane transforms."""
+    wcs = kappa.wcs
+    g = Geometry.get(kappa.shape, wcs)
+    own = modlmap is None or (np.shape(modlmap) == g.shape and np.array_equal(np.asarray(modlmap), g.modlmap()))
+    if own and not return_fphi:
+        lp = _LensPlan.get(kappa.shape, wcs)
+        a, loc, _keep = _f64_in(kappa)
+        out, optr, oloc = _enmap.result_map(g.shape, np.float64, wcs)
+        check(lib.ox_lens_kappa_to_phi(lp.handle, a, loc, optr, oloc))
+        return out
     f = _fft or _C2C(g)
-    pix = _enmap.pixsize(g.shape, kappa.wcs, method=g.method)
-    fphi = fkappa_to_fphi(f(np.asarray(kappa), scale=float(np.sqrt(pix / g.npix))), modlmap)
-    phi = ndmap(f(fphi, inverse=True, scale=float(1.0 / np.sqrt(pix * g.npix))).real, kappa.wcs)
-    return (phi, ndmap(fphi, kappa.wcs)) if return_fphi else phi
+    pix = _enmap.pixsize(g.shape, wcs, method=g.method)
+    fphi = fkappa_to_fphi(f(np.asarray(kappa), scale=float(np.sqrt(pix / g.npix))), np.asarray(modlmap))
+    phi = ndmap(f(fphi, inverse=True, scale=float(1.0 / np.sqrt(pix * g.npix))).real, wcs)
+    return (phi, ndmap(fphi, wcs)) if return_fphi else phi
+
+
+def alpha_from_kappa(kappa=None, posmap=None, phi=None, grad=True):
+    """Deflection field grad(phi) as (2, Ny, Nx) = (d/dy, d/dx) in radians (lensing.py:443-454, grad=True branch), by
+    FFT on the device.  (The reference differentiates with enmap.grad, also a Fourier derivative.)"""
+    if not grad:
+        raise NotImplementedError("alpha_from_kappa(grad=False) (pixel positions through pixell's sky2pix) is outside the accelerated path")
+    if phi is None:
+        phi = kappa_to_phi(kappa, None)
+    wcs = phi.wcs
+    lp = _LensPlan.get(phi.shape, wcs)
+    a, loc, _keep = _f64_in(phi)
+    check(lib.ox_lens_set_phi(lp.handle, a, loc))
+    out, optr, oloc = _enmap.result_map((2,) + lp.geometry.shape, np.float64, wcs)
+    check(lib.ox_lens_alpha(lp.handle, optr, oloc))
+    return out
 
 
 def flat_taylens(phi, imap, taylor_order=5, _fft=None):
-    """Lens imap by the potential phi with the Taylens algorithm (lensing.py:395-440): nearest-pixel
-    remap plus a Taylor series in the sub-pixel deflection, every derivative an inverse FFT (device)."""
-    from math import factorial, comb
-    g = Geometry.get(phi.shape, phi.wcs)
-    f = _fft or _C2C(g, nplanes=taylor_order + 1)
-    Ny, Nx = g.shape
-    ly_array, lx_array = np.meshgrid(g.ly, g.lx, indexing="ij")
-    kphi = f(np.asarray(phi))
-    alpha = f(np.stack([1j * lx_array * kphi, 1j * ly_array * kphi]), inverse=True).real
-    alphaX, alphaY = alpha
-    iy, ix = np.mgrid[0:Ny, 0:Nx]
-    ext = _enmap.extent(g.shape, phi.wcs, method=g.method)
-    py, px = ext[0] / Ny, ext[1] / Nx
-    alphaX0 = np.array(np.round(alphaX / px), dtype='int64')
-    alphaY0 = np.array(np.round(alphaY / py), dtype='int64')
-    delta_alphaX = alphaX - alphaX0 * px
-    delta_alphaY = alphaY - alphaY0 * py
-    sy, sx = (iy + alphaY0) % Ny, (ix + alphaX0) % Nx
-    lensed = np.asarray(imap)[sy, sx].astype(np.float64)
-    kmap = f(np.asarray(imap))
-    for n in range(1, taylor_order):
-        facs = np.stack([1j ** n * comb(n, k) * lx_array ** (n - k) * ly_array ** k / factorial(n) * kmap for k in range(n + 1)])
-        derivs = f(facs, inverse=True).real
-        for k in range(n + 1):
-            lensed += derivs[k][sy, sx] * delta_alphaX ** (n - k) * delta_alphaY ** k
-    return ndmap(lensed, getattr(imap, "wcs", phi.wcs))
+    """Lens imap by the potential phi with the Taylens algorithm (lensing.py:395-440): nearest-pixel remap plus a
+    Taylor series in the sub-pixel deflection.  Everything runs on the device (ox_lens_set_phi / ox_lens_taylens):
+    the deflection and every derivative are half-plane inverse transforms, the remap and the series one gather
+    kernel per order."""
+    wcs = phi.wcs
+    g = Geometry.get(phi.shape, wcs)
+    if tuple(np.shape(imap)[-2:]) != g.shape:
+        raise ValueError(f"imap of shape {np.shape(imap)} does not match phi {g.shape}")
+    lp = _LensPlan.get(phi.shape, wcs, max_planes=max(8, int(taylor_order)))
+    a, loc, _kp = _f64_in(phi)
+    check(lib.ox_lens_set_phi(lp.handle, a, loc))
+    return _taylens_current(lp, imap, taylor_order, getattr(imap, "wcs", wcs))
+
+
+def _taylens_current(lp, imap, taylor_order, wcs):
+    nmaps = int(np.prod(np.shape(imap)[:-2], dtype=np.int64)) if np.ndim(imap) > 2 else 1
+    a, loc, _ki = _f64_in(imap)
+    out, optr, oloc = _enmap.result_map(np.shape(imap), np.float64, wcs)
+    check(lib.ox_lens_taylens(lp.handle, a, loc, nmaps, int(taylor_order), optr, oloc))
+    return out
+
+
+def displace_map(imap, phi=None, order=3, _plan=None):
+    """Stand-in for pixell.lensing.displace_map(imap, alpha_pix, order) as FlatLensingSims calls it (lensing.py:512):
+    the map interpolated at the positions displaced by grad(phi), periodic boundaries, bicubic (Keys a = -1/2)
+    convolution on the device (ox_lens_displace).  pixell interpolates with prefiltered splines of order
+    ``order``; only order=3 (cubic) has a device kernel here and the two cubic schemes differ at the 1e-3 level of the
+    map's small-scale power (not a parity path: pixell is absent from the reference snapshot)."""
+    if order != 3:
+        raise NotImplementedError("displace_map: the device kernel is bicubic (order=3); use flat_taylens for higher orders")
+    wcs = getattr(imap, "wcs", None) if phi is None else phi.wcs
+    lp = _plan or _LensPlan.get(np.shape(imap), wcs)
+    if phi is not None:
+        a, loc, _kp = _f64_in(phi)
+        check(lib.ox_lens_set_phi(lp.handle, a, loc))
+    nmaps = int(np.prod(np.shape(imap)[:-2], dtype=np.int64)) if np.ndim(imap) > 2 else 1
+    a, loc, _ki = _f64_in(imap)
+    out, optr, oloc = _enmap.result_map(np.shape(imap), np.float64, getattr(imap, "wcs", wcs))
+    check(lib.ox_lens_displace(lp.handle, a, loc, nmaps, optr, oloc))
+    return out
 
 
 def get_central(img, fracy, fracx=None):
@@ -433,13 +510,16 @@ def get_central(img, fracy, fracx=None):
 
 
 class FlatLensingSims(object):
-    """lensing.py:458-521: unlensed GRF -> lensing -> beam -> + noise GRF, every step on the device.
-    The reference remaps with pixell.lensing.displace_map (spline interpolation, out of the path's
-    scope); here the lensing step is the reference's own FFT-based flat_taylens
-    (lensing.py:395-440) with taylor_order = lens_order."""
+    """lensing.py:458-521: unlensed GRF -> lensing -> beam -> + noise GRF.  Every step between the seeds and
+    ``observed`` runs on the device and the maps handed from step to step stay in HBM (enmap.devmap): MapGen.get_map
+    x3, kappa_to_phi, the lensing operation, filter_map (one fused r2c -> beam -> c2r pass) and the final sum.
+    The reference remaps with pixell.lensing.displace_map (spline interpolation of order lens_order; third party,
+    absent from the snapshot).  lensing="taylens" (default) uses the reference's own FFT-based flat_taylens
+    (lensing.py:395-440) with taylor_order = lens_order; lensing="bicubic" uses the bicubic displacement kernel
+    (displace_map above).  noise: the MapGens' noise source ("numpy" = the reference's seeds, "philox" = device)."""
 
     def __init__(self, shape, wcs, theory, beam_arcmin, noise_uk_arcmin, noise_e_uk_arcmin=None, noise_b_uk_arcmin=None,
-                 pol=False, fixed_lens_kappa=None):
+                 pol=False, fixed_lens_kappa=None, lensing="taylens", noise="numpy"):
         from . import maps, cosmology
         if len(shape) < 3 and pol:
             shape = (3,) + tuple(shape)
@@ -447,14 +527,17 @@ class FlatLensingSims(object):
             noise_e_uk_arcmin = np.sqrt(2.) * noise_uk_arcmin
         if noise_b_uk_arcmin is None:
             noise_b_uk_arcmin = noise_e_uk_arcmin
+        if lensing not in ("taylens", "bicubic"):
+            raise ValueError("lensing must be 'taylens' or 'bicubic'")
+        self.lensing = lensing
         self.shape, self.wcs = tuple(shape), wcs
         self.geometry = Geometry.get(shape, wcs)
         self.modlmap = ndmap(self.geometry.modlmap(), wcs)
         Ny, Nx = shape[-2:]
         ells = np.arange(0, self.modlmap.max(), 1)
         ps_cmb = cosmology.power_from_theory(ells, theory, lensed=False, pol=pol)
-        self.mgen = maps.MapGen(shape, wcs, ps_cmb)
-        self._fft = _C2C(self.geometry, nplanes=8)
+        self.mgen = maps.MapGen(shape, wcs, ps_cmb, noise=noise)
+        self._lp = _LensPlan.get(shape, wcs)
         self._fc = maps.FourierCalc(shape, wcs)
         if fixed_lens_kappa is not None:
             self._fixed = True
@@ -462,21 +545,25 @@ class FlatLensingSims(object):
         else:
             self._fixed = False
             ps_kk = theory.gCl('kk', self.modlmap).reshape((1, 1, Ny, Nx))
-            self.kgen = maps.MapGen(shape[-2:], wcs, ps_kk)
+            self.kgen = maps.MapGen(shape[-2:], wcs, ps_kk, noise=noise)
             self.ps_kk = ps_kk
         self.kbeam = maps.gauss_beam(self.modlmap, beam_arcmin)
+        self._kbeam_dev = _enmap.to_device(np.asarray(self.kbeam), np.float64, wcs) if _enmap.DEVICE_RESIDENT else self.kbeam
         ncomp = 3 if pol else 1
         ps_noise = np.zeros((ncomp, ncomp, Ny, Nx))
         ps_noise[0, 0] = (noise_uk_arcmin * np.pi / 180. / 60.) ** 2.
         if pol:
             ps_noise[1, 1] = (noise_e_uk_arcmin * np.pi / 180. / 60.) ** 2.
             ps_noise[2, 2] = (noise_b_uk_arcmin * np.pi / 180. / 60.) ** 2.
-        self.ngen = maps.MapGen(shape, wcs, ps_noise)
+        self.ngen = maps.MapGen(shape, wcs, ps_noise, noise=noise)
         self.ps_noise = ps_noise
 
     def update_kappa(self, kappa):
         self.kappa = kappa
-        self.phi = kappa_to_phi(ndmap(np.asarray(kappa), self.wcs), self.modlmap, _fft=self._fft)
+        k = kappa if isinstance(kappa, devmap) else ndmap(np.asarray(kappa), self.wcs)
+        self.phi = kappa_to_phi(k, None)
+        a, loc, _keep = _f64_in(self.phi)
+        check(lib.ox_lens_set_phi(self._lp.handle, a, loc))     # the deflection and its Taylens split stay in the plan
 
     def get_unlensed(self, seed=None):
         return self.mgen.get_map(seed=seed)
@@ -490,7 +577,7 @@ class FlatLensingSims(object):
         unlensed = self.get_unlensed(seed_cmb)
         if skip_lensing:
             lensed = unlensed
-            kappa = ndmap(np.asarray(lensed).reshape((-1,) + self.geometry.shape)[0] * 0, self.wcs)
+            kappa = ndmap(np.zeros(self.geometry.shape), self.wcs)
         else:
             if not (self._fixed):
                 kappa = self.get_kappa(seed_kappa)
@@ -498,12 +585,15 @@ class FlatLensingSims(object):
             else:
                 kappa = None
                 assert seed_kappa is None
-            comps = np.asarray(unlensed).reshape((-1,) + self.geometry.shape)
-            lensed = np.stack([flat_taylens(self.phi, ndmap(c, self.wcs), taylor_order=lens_order, _fft=self._fft) for c in comps])
-            lensed = ndmap(lensed.reshape(np.shape(unlensed)), self.wcs)
-        beamed = maps.filter_map(lensed, self.kbeam, self._fc)
+            if self.lensing == "taylens":
+                lensed = _taylens_current(self._lp, unlensed, lens_order, self.wcs)
+            else:
+                lensed = displace_map(unlensed, None, order=3, _plan=self._lp)
+        beamed = maps.filter_map(lensed, self._kbeam_dev, self._fc)
         noise_map = self.ngen.get_map(seed=seed_noise)
-        observed = ndmap(np.asarray(beamed) + np.asarray(noise_map), self.wcs)
+        observed = beamed + noise_map
+        if not isinstance(observed, devmap):
+            observed = ndmap(np.asarray(observed), self.wcs)
         if return_intermediate:
             return [get_central(x, cfrac) if x is not None else None for x in [unlensed, kappa, lensed, beamed, noise_map, observed]]
         return get_central(observed, cfrac)

@@ -229,6 +229,21 @@ def test_flat_lensing_sims_match_oracle(pol, theory):
     assert relerr(lens, olens) < TOL64                          # identical inputs: the transform chain itself
     skipped = sims.get_sim(seed_cmb=1, seed_noise=3, skip_lensing=True, cfrac=0.5)
     assert skipped.shape[-2:] == (64, 64)
+    # deflection field and the bicubic displacement (the stand-in for pixell's displace_map) against their numpy
+    # definitions, on identical inputs
+    ophi = oenmap.ndmap(np.asarray(phi), wo)
+    alpha = lensing.alpha_from_kappa(phi=maps.ndmap(np.asarray(phi), wcs))
+    assert relerr(alpha, lensing_np.grad_phi(ophi)) < TOL64
+    cmb = np.asarray(want[0])
+    disp = lensing.displace_map(maps.ndmap(cmb, wcs), maps.ndmap(np.asarray(phi), wcs), order=3)
+    odisp = lensing_np.displace_bicubic(cmb, ophi)
+    assert np.shape(disp) == np.shape(cmb) and relerr(disp, odisp) < TOL64
+    # the two lensing operations agree where they should: to the interpolation error of a cubic on these maps
+    tay = lensing.flat_taylens(maps.ndmap(np.asarray(phi), wcs), maps.ndmap(cmb, wcs), 5)
+    assert relerr(disp, tay) < 5e-2
+    bsims = lensing.FlatLensingSims(shape, wcs, cosmology.default_theory(), 1.5, 1.0, pol=pol, lensing="bicubic")
+    bobs = bsims.get_sim(seed_cmb=1, seed_kappa=2, seed_noise=3)
+    assert relerr(bobs, got[5]) < 5e-2
 
 
 def test_hermitian_check_is_exhaustive(theory):

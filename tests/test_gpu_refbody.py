@@ -68,7 +68,12 @@ def test_lensing_callers_match_reference_bodies():
     phi, fphi = lensing.kappa_to_phi(maps.ndmap(GL["kappa"], wcs), modl, return_fphi=True)
     assert relerr(phi, GL["phi"]) < TOL
     assert relerr(fphi, GL["fphi"]) < TOL      # carries enmap.fft(normalize='phys')'s (pixsize/Npix)^1/2
+    # the device route (half-plane transforms, ox_lens_kappa_to_phi), from a host and from a device-resident map
+    assert relerr(lensing.kappa_to_phi(maps.ndmap(GL["kappa"], wcs), modl), GL["phi"]) < TOL
+    assert relerr(lensing.kappa_to_phi(maps.devmap.from_host(GL["kappa"], wcs), modl), GL["phi"]) < TOL
     assert relerr(lensing.fkappa_to_fphi(np.fft.fft2(GL["kappa"]), modl), GL["fk2fp"]) < 1e-13
     for order in (2, 5):
         got = lensing.flat_taylens(maps.ndmap(GL["phis"], wcs), maps.ndmap(GL["imap"], wcs), order)
+        assert relerr(got, GL[f"lensed_o{order}"]) < TOL
+        got = lensing.flat_taylens(maps.devmap.from_host(GL["phis"], wcs), maps.devmap.from_host(GL["imap"], wcs), order)
         assert relerr(got, GL[f"lensed_o{order}"]) < TOL

@@ -432,7 +432,7 @@ def test_tma_row_pass_matches_the_legacy_row_pass_and_the_oracle(pol, theory, mo
         fin = np.isfinite(out["legacy"][0])
         assert np.max(np.abs(out[kb][0] - out["legacy"][0])[fin] / np.abs(out["legacy"][0])[fin].max()) < 1e-13
         assert relerr(out[kb][1], out["legacy"][1]) < 1e-13
-    bp, stored = out["w32"]       # (the default at nx = 2048: one warp per row, two radix-32 stages, ox_row_w32.cuh)
+    bp, stored = out["tma"]       # (the default)
     pairs = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)] if pol else [(0, 0)]
     auto = {0: 0, 1: 3, 2: 5}
     for i in (0, nsim - 1):
