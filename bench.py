@@ -680,12 +680,50 @@ def run_config_qe(cx, args, est, npix, dtype_name, nb, total_real, label, scalin
                                  "frac": value / cx.ws * pb / 1e9 / cx.peak,
                                  "note": ("38 s N" if est == "TT" else "76 s N") + " per realisation (SURVEY 8d: cuFFT-chain accounting, each 2-D FFT two passes)"},
            "stages": cx.stages(st_ms, alg), "cpu_baseline": None}
+    if est == "TT" and not args.no_extras:
+        res["sim_to_kappa_on_device"] = sim_to_kappa_chain(cx, args, q, shape, wcs, th, npix)
     if cpu and cx.ws == 1 and args.cpu_sample > 0:
         res["cpu_baseline"] = qe_cpu_baseline(q, est, npix, xin.array[0], None if yin is None else yin.array[0])
     for b in (X, Y, out):
         if b is not None:
             b.free()
     return res
+
+
+def sim_to_kappa_chain(cx, args, q, shape, wcs, th, npix, nreal=6):
+    """configs[3] end to end as tutorials/tt_verification.ipynb:597-617 runs it, one realisation at a time through the
+    reference signatures, every map device-resident: FlatLensingSims.get_sim (unlensed GRF -> kappa GRF -> phi -> Taylens
+    order 5 -> beam -> + noise GRF) -> FourierCalc.power2d -> qest.kappa_from_map (+ mean-field accumulate)."""
+    from orphics_b200 import maps, lensing
+    capi = cx.capi
+    t0 = time.perf_counter()
+    sims = lensing.FlatLensingSims(shape, wcs, th, 1.5, 1.0, pol=False, noise="philox")
+    fc = maps.FourierCalc(shape, wcs)
+    setup_s = time.perf_counter() - t0
+
+    def one(i, parts=None):
+        obs = sims.get_sim(seed_cmb=3 * i, seed_kappa=3 * i + 1, seed_noise=3 * i + 2, lens_order=5)
+        if parts is not None:
+            capi.synchronize()
+            parts.append(time.perf_counter())
+        _, kT, _ = fc.power2d(obs)
+        rec = q.kappa_from_map("TT", kT, alreadyFTed=True, accumulate_meanfield=True)
+        return rec
+    one(0)
+    capi.synchronize()
+    t0 = time.perf_counter()
+    for i in range(1, nreal + 1):
+        rec = one(i)
+    capi.synchronize()
+    dt = time.perf_counter() - t0
+    parts = [time.perf_counter()]
+    one(99, parts)
+    capi.synchronize()
+    parts.append(time.perf_counter())
+    chk = float(np.asarray(rec[:4, :4]).sum())
+    return {"value": nreal / dt, "unit": "realisations/s", "realisations": nreal, "setup_seconds": setup_s,
+            "ms_get_sim": 1e3 * (parts[1] - parts[0]), "ms_power2d_and_estimator": 1e3 * (parts[2] - parts[1]), "checksum": chk,
+            "note": "per-call API, device-resident maps between the calls; Taylens order 5 = 14 half-plane inverse transforms per map"}
 
 
 def qe_cpu_baseline(q, est, npix, x, y):
@@ -695,8 +733,8 @@ def qe_cpu_baseline(q, est, npix, x, y):
     from oracle import qe_np, maps_np as omaps
     so, wo = omaps.rect_geometry(width_arcmin=npix * 0.5, px_res_arcmin=0.5)
     Nn = q.N
-    tables = {"WXY_" + est: Nn.WXY(est), "WY_" + est[1] * 2: Nn.WY(est[1] * 2)}
-    qo = qe_np.qest_from_tables(so, wo, tables, {est: np.asarray(Nn.AL[est])}, Nn.fmaskK)
+    tables = {"WXY_" + est: np.asarray(Nn.WXY(est)), "WY_" + est[1] * 2: np.asarray(Nn.WY(est[1] * 2))}
+    qo = qe_np.qest_from_tables(so, wo, tables, {est: np.asarray(Nn.AL[est])}, None if Nn.fmaskK is None else np.asarray(Nn.fmaskK))
     cores = host_cores()
     x64 = np.asarray(x, dtype=np.float64)
     y64 = None if y is None else np.asarray(y, dtype=np.float64)

@@ -226,6 +226,9 @@ int ox_qe_path(ox_qeplan *q);
  * kfilter is a real float64 full-plane [ny][nx] array (beam, l-mask, Wiener filter) */
 int ox_power_filter(ox_powerplan *p, const void *maps, int where, int nbatch, const double *kfilter, int kwhere, void *out,
                     int out_where);
+/* the same with a complex128 full-plane kfilter (maps.py:1923 takes any array): out = Re ifft(fft(m) kfilter) / Npix */
+int ox_power_filter_complex(ox_powerplan *p, const void *maps, int where, int nbatch, const void *kfilter, int kwhere, void *out,
+                            int out_where);
 
 /* ---- generic batched c2c FFT on full-plane complex arrays (pixell.fft.fft / ifft, lensing.py:20):
  * out = scale * FFT_direction(in), direction -1 forward / +1 backward, nplanes arrays [ny][nx] */
@@ -261,6 +264,23 @@ int ox_ilc(const void *kmaps, const double *cinv, const double *response_a, cons
  * the symmetric n x n matrices mat[n][n][npix] (float64, n <= 4) through a Jacobi eigen-decomposition; for a
  * non-integer or negative exponent, eigenvalues that are negative or below 1e-13 of the largest are zeroed. */
 int ox_multi_pow(const double *mat, int n, long long npix, double exponent, int where, double *out, int out_where);
+
+/* ---- set-up of the estimator on the device (historical QuadNorm, call site tutorials/tt_verification.ipynb:81).
+ * All tables are float64 full planes [ny][nx] in DEVICE memory (results too); nullable ones are noted.
+ *  ox_qe_filter  out = nan_to_num(num / (lcl beam^2 + noise)) beam, zeroed where mask < 1e-3, where L > cut_gt and where
+ *                L >= cut_ge: W_XY (num = uC^{XY'}, cut_gt = gradCut, cut_ge = bigell) and W_Y (num NULL = 1, cut_gt = inf).
+ *                num, noise, beam, mask may be NULL (1, 0, 1, no mask).
+ *  ox_qe_norm    A_L of estimator est (OX_QE_TT / OX_QE_EB) from cl = uC^{TT} (uC^{EE} for EB), w1 = W_XY beam, w2 = W_Y beam:
+ *                three inverse transforms + one forward per term, 13 (TT) / 24 (EB) cuFFT c2c transforms in all;
+ *                nlkk_out = N_L^{kappa kappa} (`.N.Nlkk[XY]`), al_out = the multiplier kappa_from_map applies
+ *                (N_L 2 / (L (L+1))).  kmask_k may be NULL; pix_area = pixScaleX pixScaleY. */
+/* res_host[3] = { max |a(l) - a(-l)|, max |a|, 1.0 if the Nyquist row or column holds a non-zero } of a device plane:
+ * the test that selects the estimator's half-plane paths (symmetric filters vanishing at Nyquist) */
+int ox_plane_symmetry(ox_geometry *g, const double *a_dev, double *res_host);
+int ox_qe_filter(ox_geometry *g, const double *num, const double *lcl, const double *noise, const double *beam, const double *mask,
+                 double cut_gt, double cut_ge, double *out);
+int ox_qe_norm(ox_geometry *g, int est, const double *cl, const double *w1, const double *w2, const double *kmask_k, double bigell,
+               double pix_area, double *nlkk_out, double *al_out);
 
 /* ---- lensing of flat-sky maps (the step before the estimator in FlatLensingSims.get_sim, lensing.py:499-521).
  * A plan belongs to a geometry; py, px = pixel height and width in radians (enmap.pixshape, lensing.py:420);

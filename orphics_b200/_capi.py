@@ -119,11 +119,15 @@ SIGNATURES = {
     "ox_qe_path": [_vp],
     "ox_fft_c2c": [_vp, _vp, _i, _i, _i, _d, _vp, _i],
     "ox_power_filter": [_vp, _vp, _i, _i, _vp, _i, _vp, _i],
+    "ox_power_filter_complex": [_vp, _vp, _i, _i, _vp, _i, _vp, _i],
     "ox_split_calc": [_vp, _vp, _vp, _vp, _i, _i, _i, C.c_longlong, _d, _i, _vp, _vp, _vp, _i],
     "ox_noise_from_splits": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i],
     "ox_split_lensing_combine": [_vp, _i, _i, _i, C.c_longlong, _d, _vp, _i],
     "ox_ilc": [_vp, _vp, _vp, _vp, _i, C.c_longlong, _i, _i, _vp, _i],
     "ox_multi_pow": [_vp, _i, C.c_longlong, _d, _i, _vp, _i],
+    "ox_plane_symmetry": [_vp, _vp, _vp],
+    "ox_qe_filter": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp],
+    "ox_qe_norm": [_vp, _i, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp],
     "ox_lensplan_create": [_vp, _d, _d, _i, _pvp],
     "ox_lensplan_destroy": [_vp],
     "ox_lens_kappa_to_phi": [_vp, _vp, _i, _vp, _i],

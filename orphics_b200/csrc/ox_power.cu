@@ -205,6 +205,24 @@ __global__ void filter_half_kernel(T2 *__restrict__ kh, const double *__restrict
   kh[m * nh + i] = z;
 }
 
+// the same with a complex filter (maps.py:1923 accepts any array): Hermitian part of k f = k(p) 1/2 [f(p) + conj f(p')]
+template <typename T2>
+__global__ void filter_half_complex_kernel(T2 *__restrict__ kh, const double2 *__restrict__ f, int ny, int nx, int nxh, double invn) {
+  const long long nh = (long long)ny * nxh;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const long long m = blockIdx.y;
+  const int iy = (int)(i / nxh), ix = (int)(i - (long long)iy * nxh);
+  const int my = iy ? ny - iy : 0, mx = ix ? nx - ix : 0;
+  const double2 a = f[(long long)iy * nx + ix], b = f[(long long)my * nx + mx];
+  const double wr = 0.5 * (a.x + b.x) * invn, wi = 0.5 * (a.y - b.y) * invn;
+  T2 z = kh[m * nh + i];
+  const double zr = (double)z.x, zi = (double)z.y;
+  z.x = zr * wr - zi * wi;
+  z.y = zr * wi + zi * wr;
+  kh[m * nh + i] = z;
+}
+
 }  // namespace
 
 namespace ox {
@@ -302,6 +320,28 @@ int ox_power_filter(ox_powerplan *p, const void *maps, int where, int nbatch, co
     filter_half_kernel<double2><<<grid, PW_THREADS, 0, g_stream>>>(p->kh1.as<double2>(), (const double *)fdev, g->ny, g->nx, g->nxh, invn);
   else
     filter_half_kernel<float2><<<grid, PW_THREADS, 0, g_stream>>>(p->kh1.as<float2>(), (const double *)fdev, g->ny, g->nx, g->nxh, invn);
+  OX_KERNEL_CHECK();
+  OX_TRY(p->fft.exec_c2r(planes, p->kh1.p, p->in1.p));
+  return stage_out(out, out_where, p->in1.p, es * (size_t)planes * npix);
+}
+
+int ox_power_filter_complex(ox_powerplan *p, const void *maps, int where, int nbatch, const void *kfilter, int kwhere, void *out,
+                            int out_where) {
+  OX_REQUIRE(p && maps && kfilter && out, "ox_power_filter_complex: null pointer");
+  OX_REQUIRE(nbatch >= 1 && nbatch <= p->max_batch, "nbatch=%d outside 1..max_batch=%d", nbatch, p->max_batch);
+  ox_geometry *g = p->g;
+  size_t es = elem_size(p->dtype);
+  long long npix = (long long)g->ny * g->nx, nh = (long long)g->ny * g->nxh;
+  const void *fdev;
+  OX_TRY(stage_in(kfilter, kwhere, sizeof(double2) * npix, p->window, &fdev));
+  OX_TRY(forward_half(p, maps, where, nbatch, nullptr, p->in1, p->kh1));
+  int planes = nbatch * p->ncomp;
+  dim3 grid((unsigned)((nh + PW_THREADS - 1) / PW_THREADS), planes);
+  double invn = 1.0 / ((double)g->ny * (double)g->nx);
+  if (p->dtype == OX_F64)
+    filter_half_complex_kernel<double2><<<grid, PW_THREADS, 0, g_stream>>>(p->kh1.as<double2>(), (const double2 *)fdev, g->ny, g->nx, g->nxh, invn);
+  else
+    filter_half_complex_kernel<float2><<<grid, PW_THREADS, 0, g_stream>>>(p->kh1.as<float2>(), (const double2 *)fdev, g->ny, g->nx, g->nxh, invn);
   OX_KERNEL_CHECK();
   OX_TRY(p->fft.exec_c2r(planes, p->kh1.p, p->in1.p));
   return stage_out(out, out_where, p->in1.p, es * (size_t)planes * npix);

@@ -30,23 +30,82 @@ def _fmask(arr, mask):
     return arr
 
 
+def _dense_theory_tables(theory, L_max):
+    """1-D tables t[which+key][l], l = 0..lmax, equal to theory.lCl / uCl on a dense integer grid, when the theory is
+    piecewise linear between integer knots (the CAMB tables, cosmology.py:888-943): linear interpolation of the dense
+    tables at |l| is then the theory's own interpolation.  None when that cannot be guaranteed."""
+    from .cosmology import TheorySpectra
+    if not isinstance(theory, TheorySpectra):
+        return None
+    out, lo = {}, None
+    for which in ("l", "u"):
+        for key in ("TT", "EE", "BB", "TE"):
+            if key not in theory._tables[which]:
+                return None
+            x, y = theory._tables[which][key]
+            if x.size < 2 or np.any(x != np.round(x)) or np.any(np.diff(x) <= 0):
+                return None
+            hi = int(min(x[-1], np.ceil(L_max) + 1))
+            ell = np.arange(0, hi + 1, dtype=np.float64)
+            out[which + key] = np.interp(ell, x, y, left=0., right=0.)
+            lo = x[0] if lo is None else max(lo, x[0])
+    return out, lo
+
+
 class QuadNorm(object):
-    """Filters W_XY, W_Y and the normalisation on the 2-D Fourier grid (historical QuadNorm)."""
+    """Filters W_XY, W_Y and the normalisation on the 2-D Fourier grid (historical QuadNorm).
+
+    Device set-up (default): the 2-D spectra are interpolated on the device, the filters are one kernel each
+    (ox_qe_filter) and A_L is 13 / 24 cuFFT transforms with the products between them in HBM (ox_qe_norm); the
+    tables are device-resident maps that turn into numpy arrays on host access.  ORPHX_QE_SETUP=host (or a theory
+    object that is not the package's piecewise-linear TheorySpectra) keeps the numpy arithmetic of round 1."""
 
     def __init__(self, shape, wcs, theory, noise2d, noise2d_P, noise2d_B, beam2d, kmask, kmask_P, kmask_K, grad_cut,
                  unlensed_equals_lensed, bigell, geometry, fft_plan):
+        import os
         g = self.geometry = geometry
         self._plan = fft_plan
         self.shape, self.wcs = tuple(shape[-2:]), wcs
-        self.lyMap, self.lxMap = np.meshgrid(g.ly, g.lx, indexing="ij")
-        self.modLMap = g.modlmap()
-        with np.errstate(divide="ignore", invalid="ignore"):
-            inv = np.nan_to_num(1. / self.modLMap, posinf=0., neginf=0.)
-        self.lxHatMap, self.lyHatMap = self.lxMap * inv, self.lyMap * inv
         ext = _enmap.extent(g.shape, wcs, method=g.method)
         self.pixScaleY, self.pixScaleX = ext[0] / g.shape[0], ext[1] / g.shape[1]
         self.bigell = bigell
         self.gradCut = bigell if grad_cut is None else grad_cut
+        self.Nlkk, self.AL = {}, {}
+        self._lazy = {}
+        dense = None
+        if _enmap.DEVICE_RESIDENT and os.environ.get("ORPHX_QE_SETUP", "device") != "host":
+            lmax = float(np.hypot(np.abs(g.ly).max(), np.abs(g.lx).max()))
+            dense = _dense_theory_tables(theory, lmax)
+            if dense is not None:
+                # no pixel may fall strictly between 0 and the first knot, where the dense table ramps and the theory is 0
+                nz = np.concatenate([np.abs(g.ly)[np.abs(g.ly) > 0], np.abs(g.lx)[np.abs(g.lx) > 0]])
+                if nz.size and nz.min() < dense[1]:
+                    dense = None
+        self.device = dense is not None
+        if self.device:
+            tabs = dense[0]
+            keys = ("TT", "EE", "BB", "TE")
+            n = max(t.size for t in tabs.values())
+            stack = np.zeros((8, n))
+            for i, k in enumerate(keys):
+                stack[i, :tabs["l" + k].size] = tabs["l" + k]
+                stack[4 + i, :tabs["u" + k].size] = tabs["u" + k]
+            planes = devmap.empty((8,) + g.shape, np.float64, wcs)
+            check(lib.ox_geometry_interp_spec(g.handle, ptr(stack), 8, n, C.c_void_p(planes.ptr), _capi.OX_DEVICE))
+            self.lClFid2d = {k: planes[i] for i, k in enumerate(keys)}
+            self.uClFid2d = dict(self.lClFid2d) if unlensed_equals_lensed else {k: planes[4 + i] for i, k in enumerate(keys)}
+            up = lambda a: _enmap.to_device(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), g.shape)), np.float64, wcs)
+            self.noise = {"TT": None if noise2d is None else up(noise2d)}
+            if noise2d_P is not None:
+                self.noise["EE"] = up(noise2d_P)
+            else:
+                self.noise["EE"] = None if self.noise["TT"] is None else self.noise["TT"] * 2.
+            self.noise["BB"] = self.noise["EE"] if noise2d_B is None else up(noise2d_B)
+            self.kBeam = None if beam2d is None else up(beam2d)
+            self.fMask = {"TT": None if kmask is None else up(kmask), "EE": None if kmask_P is None else up(kmask_P)}
+            self.fMask["BB"] = self.fMask["EE"]
+            self.fmaskK = None if kmask_K is None else up(kmask_K)
+            return
         L = self.modLMap
         self.uClFid2d = {k: (theory.lCl(k, L) if unlensed_equals_lensed else theory.uCl(k, L)) for k in ("TT", "EE", "BB", "TE")}
         self.lClFid2d = {k: theory.lCl(k, L) for k in ("TT", "EE", "BB", "TE")}
@@ -57,7 +116,23 @@ class QuadNorm(object):
         self.kBeam = z + (1. if beam2d is None else beam2d)
         self.fMask = {"TT": kmask, "EE": kmask_P, "BB": kmask_P}
         self.fmaskK = kmask_K
-        self.Nlkk, self.AL = {}, {}
+
+    # 2-D coordinate arrays of the host route, built on first use (the device route never needs them)
+    def _coord(self, name):
+        if name not in self._lazy:
+            g = self.geometry
+            lyMap, lxMap = np.meshgrid(g.ly, g.lx, indexing="ij")
+            modL = g.modlmap()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = np.nan_to_num(1. / modL, posinf=0., neginf=0.)
+            self._lazy.update(lyMap=lyMap, lxMap=lxMap, modLMap=modL, lxHatMap=lxMap * inv, lyHatMap=lyMap * inv)
+        return self._lazy[name]
+
+    lyMap = property(lambda self: self._coord("lyMap"))
+    lxMap = property(lambda self: self._coord("lxMap"))
+    modLMap = property(lambda self: self._coord("modLMap"))
+    lxHatMap = property(lambda self: self._coord("lxHatMap"))
+    lyHatMap = property(lambda self: self._coord("lyHatMap"))
 
     # device transforms of full-plane complex arrays: raw forward, backward / Npix (lensing.py:20)
     def _fft(self, a, inverse=False):
@@ -68,10 +143,19 @@ class QuadNorm(object):
         check(lib.ox_fft_c2c(self._plan, ptr(a), OX_HOST, nplanes, 1 if inverse else -1, scale, ptr(out), OX_HOST))
         return out
 
+    def _filter_dev(self, num, XX, cut_gt):
+        p = lambda m: None if m is None else C.c_void_p(m.ptr)
+        out = devmap.empty(self.shape, np.float64, self.wcs)
+        check(lib.ox_qe_filter(self.geometry.handle, p(num), p(self.lClFid2d[XX]), p(self.noise[XX]), p(self.kBeam), p(self.fMask[XX]),
+                               C.c_double(cut_gt), C.c_double(self.bigell), C.c_void_p(out.ptr)))
+        return out
+
     def WXY(self, XY):
         X, Y = XY
         if Y == 'B':
             Y = 'E'
+        if self.device:
+            return self._filter_dev(self.uClFid2d[X + Y], X + X, float(self.gradCut))
         with np.errstate(divide="ignore", invalid="ignore"):
             tot = self.lClFid2d[X + X] * self.kBeam ** 2. + self.noise[X + X]
             W = _fmask(np.nan_to_num(self.uClFid2d[X + Y] / tot, posinf=0., neginf=0.) * self.kBeam, self.fMask[X + X])
@@ -80,6 +164,8 @@ class QuadNorm(object):
         return W
 
     def WY(self, YY):
+        if self.device:
+            return self._filter_dev(None, YY, float("inf"))
         with np.errstate(divide="ignore", invalid="ignore"):
             tot = self.lClFid2d[YY] * self.kBeam ** 2. + self.noise[YY]
             W = _fmask(np.nan_to_num(1. / tot, posinf=0., neginf=0.) * self.kBeam, self.fMask[YY])
@@ -87,6 +173,20 @@ class QuadNorm(object):
         return W
 
     def getNlkk2d(self, XY):
+        if XY not in ('TT', 'EB'):
+            raise NotImplementedError(f"estimator {XY!r} (TT and EB are on the accelerated path)")
+        if self.device:
+            W1, W2 = self.WXY(XY), self.WY('TT' if XY == 'TT' else 'BB')
+            if self.kBeam is not None:
+                W1, W2 = W1 * self.kBeam, W2 * self.kBeam
+            Cl = self.uClFid2d['TT' if XY == 'TT' else 'EE']
+            nl = devmap.empty(self.shape, np.float64, self.wcs)
+            al = devmap.empty(self.shape, np.float64, self.wcs)
+            check(lib.ox_qe_norm(self.geometry.handle, _capi.QE_TT if XY == 'TT' else _capi.QE_EB, C.c_void_p(Cl.ptr), C.c_void_p(W1.ptr),
+                                 C.c_void_p(W2.ptr), None if self.fmaskK is None else C.c_void_p(self.fmaskK.ptr),
+                                 C.c_double(self.bigell), C.c_double(self.pixScaleX * self.pixScaleY), C.c_void_p(nl.ptr), C.c_void_p(al.ptr)))
+            self.Nlkk[XY], self.AL[XY] = nl, al
+            return al
         lx, ly, L = self.lxMap, self.lyMap, self.modLMap
         ifft = lambda a: self._fft(a, inverse=True)
         if XY == 'TT':
@@ -98,7 +198,7 @@ class QuadNorm(object):
             for ell1, ell2 in ((lx, lx), (ly, ly), (rfact * lx, rfact * ly)):
                 f = ifft(np.stack([ell1 * ell2 * Cl * WXY, ell1 * WXY, ell2 * Cl * WY]))
                 acc = acc + ell1 * ell2 * self._fft(f[0] * g0 + f[1] * f[2])
-        elif XY == 'EB':
+        else:
             Cl = self.uClFid2d['EE']
             s2, c2 = 2. * self.lxHatMap * self.lyHatMap, self.lyHatMap ** 2 - self.lxHatMap ** 2
             fF = (s2 ** 2., c2 ** 2., 1.j * np.sqrt(2.) * s2 * c2)
@@ -109,8 +209,6 @@ class QuadNorm(object):
             for ellsq in (lx * lx, ly * ly, np.sqrt(2.) * lx * ly):
                 fs = ifft(np.stack([ellsq * Cl * WXY * a for a in fF]))
                 acc = acc + ellsq * self._fft(fs[0] * gs[0] + fs[1] * gs[1] + fs[2] * gs[2])
-        else:
-            raise NotImplementedError(f"estimator {XY!r} (TT and EB are on the accelerated path)")
         with np.errstate(divide="ignore", invalid="ignore"):
             alval = np.nan_to_num(1. / np.real(acc), posinf=0., neginf=0.)
         alval = _fmask(alval, self.fmaskK)
@@ -154,17 +252,32 @@ class qest(object):
     def _make_plan(self, XY):
         N = self.N
         AL = N.AL[XY] if XY in N.AL else N.getNlkk2d(XY)
+        ny, nx = self.geometry.shape
+        h = C.c_void_p()
+        est = _capi.QE_TT if XY == 'TT' else _capi.QE_EB
+        if getattr(N, "device", False) and isinstance(AL, devmap):
+            # tables stay in HBM: filters, the masked normalisation, the symmetry test that selects the half-plane paths
+            wxy, wy = N.WXY(XY), N.WY(XY[1] + XY[1])
+            norm = AL                      # (ox_qe_norm has applied kmask_K and nan_to_num already)
+
+            def sym(a, rtol):
+                r = (C.c_double * 3)()
+                check(lib.ox_plane_symmetry(self.geometry.handle, C.c_void_p(a.ptr), r))
+                return r[0] <= rtol * r[1], r[2] != 0.0
+            (s1, n1), (s2, n2), (s3, _) = sym(wxy, 0.), sym(wy, 0.), sym(norm, 1e-12)
+            real_path = s1 and s2 and s3 and not ((ny % 2 == 0 or nx % 2 == 0) and (n1 or n2))
+            check(lib.ox_qeplan_create(self.geometry.handle, est, C.c_void_p(wxy.ptr), C.c_void_p(wy.ptr), C.c_void_p(norm.ptr),
+                                       _capi.OX_DEVICE, self.dtype, self.max_batch, int(real_path), C.byref(h)))
+            self._plans[XY] = (h, real_path)
+            return
         wxy = np.ascontiguousarray(N.WXY(XY), dtype=np.float64)
         wy = np.ascontiguousarray(N.WY(XY[1] + XY[1]), dtype=np.float64)
-        norm = np.ascontiguousarray(_fmask(np.nan_to_num(AL), N.fmaskK), dtype=np.float64)
-        ny, nx = self.geometry.shape
+        norm = np.ascontiguousarray(_fmask(np.nan_to_num(np.asarray(AL)), N.fmaskK), dtype=np.float64)
         # symmetric filters that vanish on the Nyquist row/column: Hermitian inputs (transforms of real maps)
         # give real fields, so TT -- and EB, split into real and imaginary parts -- run on half planes
         real_path = (_symmetric(wxy) and _symmetric(wy) and _symmetric(norm, 1e-12)
                      and (ny % 2 or not (wxy[ny // 2].any() or wy[ny // 2].any()))
                      and (nx % 2 or not (wxy[:, nx // 2].any() or wy[:, nx // 2].any())))
-        h = C.c_void_p()
-        est = _capi.QE_TT if XY == 'TT' else _capi.QE_EB
         check(lib.ox_qeplan_create(self.geometry.handle, est, ptr(wxy), ptr(wy), ptr(norm), OX_HOST, self.dtype,
                                    self.max_batch, int(real_path), C.byref(h)))
         self._plans[XY] = (h, real_path)

@@ -239,8 +239,19 @@ class MapGen(object):
     def get_map(self, seed=None, scalar=False, iau=False, real=False, harm=False):
         """maps.py:1576-1587."""
         if real:
-            raise NotImplementedError("real=True (white noise drawn in real space) is outside the accelerated path")
-        out = self._generate([seed], self._flags(scalar, iau, harm))[0]
+            # maps.py:1578: rand = enmap.fft(enmap.rand_gauss(shape, wcs)) -- one real white-noise draw, unitary transform
+            # (on the device), handed to the generator as its harmonic noise
+            if seed is not None:
+                np.random.seed(seed)
+            shp = self.shape if len(self.shape) > 2 else self.shape[-2:]
+            white = np.random.standard_normal(shp).reshape((self.ncomp,) + self.geometry.shape)
+            if getattr(self, "_noise_fc", None) is None:
+                self._noise_fc = FourierCalc((self.ncomp,) + self.geometry.shape if self.ncomp > 1 else self.geometry.shape, self.wcs)
+            k = np.asarray(self._noise_fc.iqu2teb(white if self.ncomp > 1 else white[0], normalize=True, rot=False))
+            k = k.reshape((self.ncomp,) + self.geometry.shape)
+            out = self._generate([None], self._flags(scalar, iau, harm), noise_mode="numpy", noise_arrays=np.stack([k.real, k.imag])[None])[0]
+        else:
+            out = self._generate([seed], self._flags(scalar, iau, harm))[0]
         if len(self.shape) == 2:
             out = out[0]
         return out if isinstance(out, devmap) else ndmap(out, self.wcs)
@@ -330,12 +341,16 @@ class FourierCalc(object):
 
     def iqu2teb(self, emap, nthread=0, normalize=True, rot=True):
         """2-D FFT of the map(s) with the QU->EB rotation (maps.py:1609-1617). nthread is ignored."""
-        if normalize not in (True, False):
-            raise NotImplementedError("normalize='phys' is outside the accelerated path")
+        phys = isinstance(normalize, str) and normalize in ("phy", "phys", "physical")     # enmap.fft's spellings
+        if not phys and normalize not in (True, False):
+            raise ValueError(f"normalize={normalize!r}")
         a, loc, nc, _keep = self._as_stack(emap)
         out, optr, oloc = result_map(np.shape(emap), _capi.np_cdtype(self.dtype), self.wcs)
         flags = self._flags(rot=rot and nc == 3, normalize=bool(normalize))
         check(lib.ox_power_fft(self._plan(nc), a, loc, 1, flags, optr, oloc))
+        if phys:
+            # enmap.fft(normalize="phys") = the unitary transform x pixsize^1/2 (lensing.py:403, 653)
+            out = out * float(np.sqrt(self.geometry.area / self.geometry.npix))
         return out
 
     def f2power(self, kmap1, kmap2, pixel_units=False):
@@ -644,9 +659,17 @@ def cilc_noise(cinv, response_a, response_b):
 def filter_map(imap, kfilter, fc=None):
     """Re(ifft(fft(imap) * kfilter)) / Npix (maps.py:1922-1923)."""
     fc = FourierCalc(imap.shape, imap.wcs) if fc is None else fc
-    if np.iscomplexobj(kfilter):
-        raise NotImplementedError("filter_map: complex kfilter is outside the accelerated path")
     a, loc, nc, _keep = fc._as_stack(imap)
+    if np.issubdtype(getattr(kfilter, "dtype", np.asarray(kfilter).dtype), np.complexfloating):
+        # Re(ifft(fft(m) f)) keeps k(p) 1/2 [f(p) + conj f(p')]: the same fused pass with a complex multiplier
+        if isinstance(kfilter, devmap) and kfilter.dtype == np.complex128 and kfilter.shape == fc.geometry.shape:
+            kp, kloc, _kk = C.c_void_p(kfilter.ptr), OX_DEVICE, kfilter
+        else:
+            _kk = np.ascontiguousarray(np.broadcast_to(np.asarray(kfilter, dtype=np.complex128), fc.geometry.shape))
+            kp, kloc = ptr(_kk), OX_HOST
+        out, optr, oloc = result_map(np.shape(imap), _capi.np_dtype(fc.dtype), getattr(imap, "wcs", fc.wcs))
+        check(lib.ox_power_filter_complex(fc._plan(nc), a, loc, 1, kp, kloc, optr, oloc))
+        return out
     if isinstance(kfilter, devmap) and kfilter.dtype == np.float64 and kfilter.shape == fc.geometry.shape:
         kp, kloc, _kk = C.c_void_p(kfilter.ptr), OX_DEVICE, kfilter
     else:

@@ -41,6 +41,29 @@ def test_filters_and_normalisation_match_oracle(masked, theory):
     assert q._plans["TT"][1] == masked        # half-plane path only when the filters vanish at Nyquist
 
 
+@pytest.mark.parametrize("masked", [True, False])
+def test_device_setup_matches_host_setup(masked, theory, monkeypatch):
+    """The device set-up (interpolated 2-D spectra, ox_qe_filter, ox_qe_norm: SURVEY 8f-2) against the numpy set-up of
+    round 1 (ORPHX_QE_SETUP=host) and the oracle: filters to rounding, A_L to the conditioning of its FFT convolutions,
+    same path selection, same kappa."""
+    from orphics_b200 import lensing, enmap
+    shape, wcs, so, wo, q, qo = setup(128, 2.0, theory, masked)
+    assert q.N.device and isinstance(q.N.AL["TT"], enmap.devmap)
+    monkeypatch.setenv("ORPHX_QE_SETUP", "host")
+    _, _, _, _, qh, _ = setup(128, 2.0, theory, masked)
+    assert not qh.N.device
+    for XY in ("TT", "EB"):
+        assert relerr(q.N.WXY(XY), qh.N.WXY(XY)) < 1e-14 and relerr(q.N.WXY(XY), qo.N.WXY(XY)) < 1e-14
+        YY = XY[1] + XY[1]
+        assert relerr(q.N.WY(YY), qh.N.WY(YY)) < 1e-14 and relerr(q.N.WY(YY), qo.N.WY(YY)) < 1e-14
+        assert relerr(q.N.AL[XY], qh.N.AL[XY]) < 1e-10 and relerr(q.N.Nlkk[XY], qh.N.Nlkk[XY]) < 1e-10
+        assert q.path(XY) == qh.path(XY)
+    for k in ("TT", "EE", "TE"):
+        assert relerr(q.N.lClFid2d[k], qo.N.lCl[k]) < 1e-14
+    T = np.random.RandomState(5).standard_normal(shape) * 50
+    assert relerr(q.kappa_from_map("TT", T), qh.kappa_from_map("TT", T)) < 1e-9
+
+
 @pytest.mark.parametrize("masked,npix,path", [(True, 128, "half"), (False, 128, "c2c"), (True, 512, "fused")])
 def test_tt_kappa_matches_oracle(masked, npix, path, theory):
     shape, wcs, so, wo, q, qo = setup(npix, 2.0, theory, masked)

@@ -444,3 +444,26 @@ def test_tma_row_pass_matches_the_legacy_row_pass_and_the_oracle(pol, theory, mo
             scale = np.sqrt(np.abs(want[auto[a] if pol else 0] * want[auto[c] if pol else 0]))
             ok = np.isfinite(want[s])
             assert np.max(np.abs(bp[i, s] - want[s])[ok] / scale[ok]) < TOL64
+
+
+@pytest.mark.parametrize("pol", [False, True])
+def test_reference_options_real_noise_phys_normalisation_complex_filter(pol, theory):
+    """Options of the reference signatures that round 1 refused: MapGen.get_map(real=True) (maps.py:1578: white noise drawn
+    in real space, unitary transform), FourierCalc.iqu2teb(normalize='phys') (enmap.fft's physical normalisation, used at
+    lensing.py:403,653) and maps.filter_map with a complex kfilter (maps.py:1923)."""
+    from orphics_b200 import maps
+    shape, wcs, so, wo, modl, ps = setup(96, 3.0, pol, theory)
+    og, ofc = omaps.MapGen(so, wo, ps), omaps.FourierCalc(so, wo)
+    mg = maps.MapGen(shape, wcs, covsqrt=np.asarray(og.covsqrt))
+    fc = maps.FourierCalc(shape, wcs)
+    for kw in (dict(real=True), dict(real=True, scalar=True), dict(real=True, harm=True)):
+        assert relerr(mg.get_map(seed=8, **kw), og.get_map(seed=8, **kw)) < TOL64, kw
+    m = og.get_map(seed=9)
+    for rot in (True, False):
+        got = fc.iqu2teb(maps.ndmap(np.asarray(m), wcs), normalize="phys", rot=rot)
+        assert relerr(got, ofc.iqu2teb(m, normalize="phys", rot=rot)) < TOL64
+    rng = np.random.RandomState(4)
+    kf = np.exp(-(modl / 2000.0) ** 2) * np.exp(1j * rng.uniform(0, 2 * np.pi, size=modl.shape))     # no symmetry at all
+    got = maps.filter_map(maps.ndmap(np.asarray(m), wcs), kf)
+    assert got.dtype == np.float64 and relerr(got, omaps.filter_map(m, kf)) < TOL64
+    assert relerr(maps.filter_map(maps.ndmap(np.asarray(m), wcs), kf.real + 0j), omaps.filter_map(m, kf.real)) < TOL64
