@@ -420,6 +420,17 @@ def run_headline(cx, args):
         ar_ms, _ = cx.timed(lambda k: reduce_stats(), 1)
         pipe.reset_stats()
 
+    # ---- configs[1] literal: a FIXED batch of 1024 maps shared by the GPUs (strong scaling: 16 steps on one GPU, 2 on
+    # eight), timed from the first launch to the end of the all-reduce of the Statistics triple
+    strong = None
+    if args.scaling == "weak" and not args.no_extras:
+        Ks = max(1, 1024 // (ws * B))
+        pipe.reset_stats()
+        ms_s, _ = cx.timed(lambda k: pipe.run_raw(seeds_pin.array[k % K], B, mode, flags, None), Ks, reduce_stats)
+        strong = {"maps_total": int(Ks * B * ws), "steps_per_gpu": int(Ks), "ms_total": ms_s, "value": Ks * B * ws / (ms_s / 1e3),
+                  "unit": "maps/s", "note": "strong scaling of configs[1]: 1024 maps shared by the GPUs, all-reduce included"}
+        pipe.reset_stats()
+
     # ---- end to end through the Python API with host buffers: pinned seeds in, bandpowers out, every step
     e2e = None
     if not args.no_e2e:
@@ -499,7 +510,7 @@ def run_headline(cx, args):
         "collective": {"what": "one ncclAllReduce(sum) of the packed float64 [N | SUM | CROSS] issued by liborphx.so (ox_pipeline_allreduce)",
                        "bytes": int(8 * (1 + pipe.dim + pipe.dim ** 2)), "ms": ar_ms, "nccl_version": cx.comm.nccl_version()},
         "check": {"stat_N": int(N_stat), "mean_binned_over_theory_TT": ratio},
-        "variants": variants, "pipeline_path": pipe.path,
+        "variants": variants, "strong_scaling_1024_maps": strong, "pipeline_path": pipe.path,
         "device": capi.device_name(),
     }
     return line

@@ -244,9 +244,9 @@ def test_flat_lensing_sims_match_oracle(pol, theory):
     want = osims.get_sim(1, 2, 3, lens_order=4)
     for name, a, b in zip(("unlensed", "kappa", "lensed", "beamed", "noise", "observed"), got, want):
         assert np.shape(a) == np.shape(b), name
-        assert relerr(a, b) < 1e-8, (name, relerr(a, b))       # covsqrt set-up differs at 1e-9
+        assert relerr(a, b) < TOL64, (name, relerr(a, b))
     phi = lensing.kappa_to_phi(got[1], sims.modlmap)
-    assert relerr(phi, lensing_np.kappa_to_phi(want[1], osims.modlmap)) < 1e-8
+    assert relerr(phi, lensing_np.kappa_to_phi(want[1], osims.modlmap)) < TOL64
     lens = lensing.flat_taylens(maps.ndmap(np.asarray(want[1]) * 0 + np.asarray(phi), wcs), maps.ndmap(np.asarray(want[0]).reshape((-1, 128, 128))[0], wcs), 5)
     olens = lensing_np.flat_taylens(oenmap.ndmap(np.asarray(phi), wo), oenmap.ndmap(np.asarray(want[0]).reshape((-1, 128, 128))[0], wo), 5)
     assert relerr(lens, olens) < TOL64                          # identical inputs: the transform chain itself

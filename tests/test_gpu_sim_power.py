@@ -31,23 +31,23 @@ def bp_close(a, b, tol):
 
 
 def test_covsqrt_setup_matches_oracle(theory):
-    """MapGen.__init__ (maps.py:1573, enmap.spec2flat).  The reference's mode-weighted
-    smoothing is an FFT convolution of p*l^2 over ~10 decades of dynamic range, so it is
-    only reproducible to ~1e-9 of the peak between two FFT libraries (numpy.fft in the
-    product, scipy.fft in the oracle, pyfftw in pixell); the per-pixel interpolation that
-    runs on the device is exact to 1e-13 for identical 1-D input."""
+    """MapGen.__init__ (maps.py:1573, enmap.spec2flat): the 1-D treatment (mode-weighted smoothing by FFT convolution,
+    x Npix/area, matrix power) is host set-up and bit-identical to the oracle's (same scipy.fft convolution; two
+    different FFT libraries would agree only to ~1e-9 of the peak, C_l l^2 spans ten decades); the per-pixel
+    interpolation runs on the device.  So the product's OWN set-up -> map chain is held to the path's 1e-10."""
     from orphics_b200 import maps, enmap
     for pol in (False, True):
         for npix, res in ((128, 2.0), (512, 2.0)):
             shape, wcs, so, wo, modl, ps = setup(npix, res, pol, theory)
             mg = maps.MapGen(shape, wcs, ps)
             og = omaps.MapGen(so, wo, ps)
-            assert relerr(mg.covsqrt, og.covsqrt) < 5e-9
+            assert relerr(mg.covsqrt, og.covsqrt) < 1e-12
             cov1 = oenmap.spec2flat_1d(so, wo, ps, 0.5)
             dev = enmap.Geometry.get(shape, wcs).interp_spec(cov1)
             assert relerr(dev, og.covsqrt) < 1e-13
-        # end to end from cov: a map from the product's own covsqrt vs the oracle's
-        assert relerr(mg.get_map(seed=5), og.get_map(seed=5)) < 1e-8
+        # end to end from cov: maps and bandpowers from the product's own covsqrt vs the oracle's
+        for kw in (dict(), dict(scalar=True), dict(harm=True)):
+            assert relerr(mg.get_map(seed=5, **kw), og.get_map(seed=5, **kw)) < TOL64
 
 
 @pytest.mark.parametrize("npix,res", [(512, 2.0), (96, 3.0)])
