@@ -590,7 +590,8 @@ namespace ox {
 
 bool fused_supported(int ny, int nx, int ncomp, int dtype) {
   if (!pow2(ny) || !pow2(nx)) return false;
-  if (ny < 512 || ny > 4096 || nx < 256 || nx > 8192) return false;  // K_C needs whole warps: ny/16 >= 32
+  if (ny < 512 || ny > 8192 || nx < 256 || nx > 8192) return false;  // K_C needs whole warps: ny/16 >= 32
+  if (ny == 8192 && ncomp != 1) return false;                        // (three 8192-element columns: cuFFT path)
   if (ncomp != 1 && ncomp != 3) return false;
   size_t es = dtype == OX_F32 ? 8 : 16;
   // K_A / K_C keep ncomp columns in shared memory (plus the slot sums)
@@ -717,6 +718,10 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
     break;
   switch (g->ny) {
     OX_SIMCOL(256) OX_SIMCOL(512) OX_SIMCOL(1024) OX_SIMCOL(2048) OX_SIMCOL(4096)
+    case 8192:   // (one component only: three 8192-element columns do not fit an SM's shared memory)
+      if (nc == 1) st = launch_sim_col<T, 8192, 1>(sa, fs.Ha.p, nsim, noise_mode);
+      else set_error("fused path: ny=8192 supports one component");
+      break;
     default: set_error("fused path: unsupported ny=%d", g->ny);
   }
 #undef OX_SIMCOL
@@ -771,6 +776,10 @@ static int fused_run_T(ox_pipeline *pl, int nsim, int noise_mode, const double *
     break;
   switch (g->ny) {
     OX_COLBIN(256) OX_COLBIN(512) OX_COLBIN(1024) OX_COLBIN(2048) OX_COLBIN(4096)
+    case 8192:
+      if (nc == 1) st = launch_col_bin<T, 8192, 1>(ca, pl->partial.as<double>(), nsim, nblk);
+      else set_error("fused path: ny=8192 supports one component");
+      break;
     default: set_error("fused path: unsupported ny=%d", g->ny);
   }
 #undef OX_COLBIN

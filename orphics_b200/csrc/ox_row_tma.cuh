@@ -131,6 +131,21 @@ struct RowTmaStore {
   }
 };
 
+// tile number -> (row tile, plane).  nplanes_fast > 0: planes vary fastest (CTAs resident together share the rows of a
+// batch-shared 2-D window); nplanes_fast < 0: rows vary fastest inside a plane (-nplanes_fast = row tiles per plane): the
+// 64-byte segments that neighbouring row tiles read and write in one DRAM page are touched together.
+template <typename T>
+__device__ __forceinline__ void tile_coords(const RowArgs<T> &a, int t, int nplanes, int &rowtile, int &plane) {
+  if (a.nplanes_fast < 0) {
+    const int per = -a.nplanes_fast;
+    plane = t / per;
+    rowtile = t - plane * per;
+  } else {
+    rowtile = t / nplanes;
+    plane = t - rowtile * nplanes;
+  }
+}
+
 template <int MX, int R>
 struct RowTmaCfg {
   static constexpr int NT = MX / 16, GROUP = R * NT, NTHREADS = 2 * GROUP;
@@ -169,7 +184,8 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
   auto issue = [&a, &tmap, nplanes, ntiles](unsigned char *base, int i) {
     const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
     if (t >= ntiles) return;
-    const int rowtile = (int)(t / nplanes), plane = (int)(t - (long long)rowtile * nplanes);
+    int rowtile, plane;
+    tile_coords(a, (int)t, nplanes, rowtile, plane);
     const int slot = i % 3;
     unsigned char *dst = base + slot * Cfg::SLOT;
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot;
@@ -243,8 +259,9 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     } else {
       tws.init(a.tw, a.tw_len / MX, u);
     }
-    const int rowtile = t / nplanes;
-    const long long plane = t - rowtile * nplanes;
+    int rowtile, plane_i;
+    tile_coords(a, t, nplanes, rowtile, plane_i);
+    const long long plane = plane_i;
     T2 keep[16];
     {
       const int iy0 = rowtile * R;
@@ -333,6 +350,19 @@ inline bool row_tma_enabled() {
   return !(e && !strcmp(e, "legacy"));
 }
 
+inline bool row_tma_rows_fastest(bool dflt) {
+  const char *e = getenv("ORPHX_KB_TILE_ORDER");
+  if (e && !strcmp(e, "rows")) return true;
+  if (e && !strcmp(e, "planes")) return false;
+  return dflt;
+}
+inline CUtensorMapL2promotion row_tma_l2_promotion() {
+  const char *e = getenv("ORPHX_KB_L2PROMO");
+  const int v = e ? atoi(e) : 0;
+  return v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+       : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
+
 // launches the persistent TMA row pass if this (type, size, mode) has one; *launched says whether it did
 template <typename T, int MX, int MODE>
 int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
@@ -355,7 +385,7 @@ int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
       cuuint32_t estr[3] = {1, 1, 1};
       const CUtensorMapSwizzle swz = R == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : (R == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
       CUresult r = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>((const void *)a.Hin), dims, strides, box,
-                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, row_tma_l2_promotion(),
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for the row pass %d x %d x %lld", (int)r, a.ny, MX, nplanes);
@@ -365,7 +395,9 @@ int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
       OX_TRY(set_smem(k, SMEM));
       int grid = sm_count();   // one persistent CTA per SM
       if ((long long)grid * 2 > ntiles) grid = (int)((ntiles + 1) / 2);
-      a.nplanes_fast = (int)nplanes;
+      // planes fastest: a 2-D window shared by the planes is read from DRAM once per launch (ORPHX_KB_TILE_ORDER=rows: rows
+      // fastest inside a plane)
+      a.nplanes_fast = row_tma_rows_fastest(false) ? -(a.ny / R) : (int)nplanes;   // (measured: no difference, profiles/r02_variants.txt)
       k<<<grid, Cfg::NTHREADS, SMEM, g_stream>>>(a, tmap, (int)nplanes, (int)ntiles);
       OX_KERNEL_CHECK();
       *launched = true;

@@ -336,6 +336,35 @@ def test_fused_and_cufft_paths_agree_at_2048(monkeypatch):
             assert np.max(np.abs(a[:, s] - c[:, s]) / scale) < TOL64
 
 
+def test_fused_and_cufft_paths_agree_at_8192(monkeypatch):
+    """The largest map of the BASELINE sweep (8192^2, one component): the hand-written kernels (ny = 8192 columns of 512
+    threads, nx/2 = 4096 row transforms) against the cuFFT path, bandpowers and the stored map, float64."""
+    from orphics_b200 import maps, stats, cosmology
+    th = cosmology.default_theory()
+    shape, wcs = maps.rect_geometry(width_arcmin=8192 * 0.5, px_res_arcmin=0.5)
+    g = maps.Geometry.get(shape, wcs)
+    ps = cosmology.power_from_theory(np.arange(0, g.modlmap().max() + 1, 1.0), th, lensed=True, pol=False)
+    taper = np.asarray(maps.get_taper(shape, wcs)[0])
+    out = {}
+    mg0 = maps.MapGen(shape, wcs, ps, noise="philox_hermitian", max_batch=1)
+    cs = np.asarray(mg0.covsqrt)
+    del mg0
+    for path in ("cufft", "fused"):
+        monkeypatch.setenv("ORPHX_PIPELINE", path)
+        mg = maps.MapGen(shape, wcs, covsqrt=cs, noise="philox_hermitian", max_batch=1)
+        fc = maps.FourierCalc(shape, wcs, max_batch=1)
+        b = stats.bin2D(g.modlmap(), EDGES, geometry=g)
+        pipe = maps.SimPipeline(mg, fc, b, window=taper)
+        assert pipe.path == path
+        out[path] = pipe.run([77], keep_maps=True)
+        if path == "fused":
+            stored = pipe.last_maps(1)
+            assert relerr(stored.reshape(shape), mg.get_maps([77])[0]) < TOL64
+        del pipe, mg, fc, b
+    a, c = out["fused"], out["cufft"]
+    assert np.max(np.abs(a[:, 0] - c[:, 0]) / np.abs(c[:, 0])) < TOL64
+
+
 @pytest.mark.parametrize("pol", [False, True])
 def test_fp32_fused_pipeline_philox_within_1e5(pol, theory):
     """float32 mode on the hand-written kernels (single-precision Box-Muller, FFTs and binning) against the
