@@ -1,7 +1,7 @@
 """Regenerates the committed round-2 ncu evidence under profiles/ from the scratch captures in gpurun_out/
 (tools/prof_run_r02.sh on the GPU box, plus the row-pass captures of tools/r02_run*.sh): per-kernel summaries, the launch
 list of the bench command and the per-launch DRAM traffic bench.py quotes as roofline.traffic.
-Usage: python tools/make_profiles_r02.py"""
+Usage: python tools/make_profiles_r02.py [output directory, default profiles/]"""
 import collections
 import csv
 import io
@@ -12,7 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GO = os.path.join(ROOT, "gpurun_out")
-PR = os.path.join(ROOT, "profiles")
+PR = os.path.abspath(sys.argv[1]) if len(sys.argv) > 1 else os.path.join(ROOT, "profiles")   # (on the GPU box: a directory under gpurun_out/)
+os.makedirs(PR, exist_ok=True)
 BENCH = "python bench.py --steps 2 --warmup 3 --no-e2e --cpu-sample 0 --no-extras"
 
 

@@ -13,4 +13,7 @@ ncu --set full --clock-control none --kernel-name-base demangled -k regex:"fused
 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"fused_row_kernel<double, \(int\)4096, \(int\)[0-9]+, \(int\)3>" --launch-skip 3 --launch-count 1 -o gpurun_out/prof_r02_EB64 -f $B --configs 4 > gpurun_out/ncu_r02_EB64.log 2>&1
 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"fused_col_kernel<float, \(int\)8192, \(int\)1," --launch-skip 3 --launch-count 1 -o gpurun_out/prof_r02_EB32 -f $B --configs 4 > gpurun_out/ncu_r02_EB32.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 200 -c 120 --csv --log-file gpurun_out/launches_r02_qe.csv $B --configs 3 > gpurun_out/ncu_r02_launches_qe.log 2>&1
-ls -la gpurun_out | tail -12
+# the reports together exceed what gpurun copies back (64 MiB): summarise them here, keep only the pipeline capture
+python tools/make_profiles_r02.py gpurun_out/profiles_r02 > gpurun_out/make_profiles_r02.log 2>&1
+rm -f gpurun_out/prof_r02_IQU.ncu-rep gpurun_out/prof_r02_TT.ncu-rep gpurun_out/prof_r02_EB64.ncu-rep gpurun_out/prof_r02_EB32.ncu-rep
+ls -la gpurun_out gpurun_out/profiles_r02 | tail -24
