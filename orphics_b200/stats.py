@@ -164,11 +164,14 @@ class Statistics:
     """The reduce semantics of orphics.stats.Statistics (stats.py:918-1419): per label
     N, SUM x, SUM x x^T (stats mode) or K, SUM arr (stack mode); ``allreduce`` sums them
     over the ranks of a torch.distributed process group (NCCL on GPUs, gloo on CPU) instead
-    of mpi4py.  ``comm`` is a torch.distributed process group, ``True`` for the default
+    of mpi4py -- as ONE collective of a packed buffer, whatever the number of labels.  ``comm`` is a torch.distributed process group, ``True`` for the default
     group, or None for single-process use."""
 
-    def __init__(self, comm=None, dtype=np.float64):
+    def __init__(self, comm=None, dtype=np.float64, nccl=None):
+        """nccl: optional mpi.NcclComm -- the sums then travel through ox_comm_allreduce_f64 (NCCL issued by the C
+        library); the torch.distributed group only exchanges the label metadata."""
         self.comm = comm
+        self.nccl = nccl
         self.dtype = np.dtype(dtype)
         self._n, self._sum, self._cross = {}, {}, {}
         self._k, self._stack = {}, {}
@@ -257,20 +260,43 @@ class Statistics:
                 self._stats_label(lab, d)
             for lab, shp in stack_union.items():
                 self._stack_label(lab, shp)
-            backend = dist.get_backend(group)
-            dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-
-            def red(a):
-                t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-                return t.cpu().numpy()
-            for lab in sorted(stats_union, key=repr):
-                self._n[lab] = int(red(np.array([self._n[lab]], dtype=np.int64))[0])
-                self._sum[lab] = red(self._sum[lab])
-                self._cross[lab] = red(self._cross[lab])
-            for lab in sorted(stack_union, key=repr):
-                self._k[lab] = int(red(np.array([self._k[lab]], dtype=np.int64))[0])
-                self._stack[lab] = red(self._stack[lab])
+            # ONE collective for everything (the reference issues 3 per stats label and 2 per stack label,
+            # stats.py:1215-1217, 1227-1228): [N | SUM | CROSS] of every stats label and [K | SUM] of every stack label
+            # packed into one float64 buffer (counts stay exact below 2^53)
+            slabs, klabs = sorted(stats_union, key=repr), sorted(stack_union, key=repr)
+            parts = []
+            for lab in slabs:
+                parts += [np.array([self._n[lab]], dtype=np.float64), np.asarray(self._sum[lab], dtype=np.float64).ravel(),
+                          np.asarray(self._cross[lab], dtype=np.float64).ravel()]
+            for lab in klabs:
+                parts += [np.array([self._k[lab]], dtype=np.float64), np.asarray(self._stack[lab], dtype=np.float64).ravel()]
+            packed = np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0)
+            if packed.size:
+                if self.nccl is not None:
+                    # data plane in the C ABI: upload, ncclAllReduce issued by liborphx.so, download
+                    buf = _capi.DeviceBuffer(packed.nbytes).upload(packed)
+                    self.nccl.allreduce_f64(buf.ptr, packed.size)
+                    packed = buf.download(packed.shape, np.float64)
+                    buf.free()
+                else:
+                    backend = dist.get_backend(group)
+                    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+                    t = torch.from_numpy(packed).to(dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                    packed = t.cpu().numpy()
+            o = 0
+            for lab in slabs:
+                d = stats_union[lab]
+                self._n[lab] = int(round(packed[o]))
+                self._sum[lab] = packed[o + 1:o + 1 + d].astype(self.dtype)
+                self._cross[lab] = packed[o + 1 + d:o + 1 + d + d * d].reshape(d, d).astype(self.dtype)
+                o += 1 + d + d * d
+            for lab in klabs:
+                shp = stack_union[lab]
+                m = int(np.prod(shp, dtype=np.int64))
+                self._k[lab] = int(round(packed[o]))
+                self._stack[lab] = packed[o + 1:o + 1 + m].reshape(shp).astype(self.dtype)
+                o += 1 + m
         self._reduced = True
 
     def _check(self):

@@ -56,8 +56,24 @@ q.allreduce_meanfield("TT", comm)
 acc, cnt = q.meanfield("TT")
 _capi.synchronize()
 
-ok = True
-report = {"ws": ws, "nccl": comm.nccl_version()}
+# the host-side Statistics class with the same communicator: labels on a subset of ranks (orphics/tests/test_stats.py's
+# closed forms in P), ONE packed all-reduce through ox_comm_allreduce_f64
+st = stats.Statistics(comm=True if ws > 1 else None, nccl=comm)
+for i in range(rank + 1):
+    st.add("vec", np.arange(3.0) + rank)
+    st.add_stack("map", np.full((4, 5), float(rank + 1)))
+if rank == ws - 1:
+    st.add("last_only", np.array([7.0, 9.0]))
+st.allreduce()
+P = ws
+exp_n = P * (P + 1) // 2
+exp_sum = sum((r + 1) * (np.arange(3.0) + r) for r in range(P))
+st_ok = (st.count("vec") == exp_n and np.array_equal(st._sum["vec"], exp_sum) and st.count("last_only") == 1
+         and np.array_equal(st._sum["last_only"], [7.0, 9.0]) and st.stack_count("map") == exp_n
+         and np.array_equal(st._stack["map"], np.full((4, 5), float(sum((r + 1) ** 2 for r in range(P))))))
+
+ok = bool(st_ok)
+report = {"ws": ws, "nccl": comm.nccl_version(), "statistics_class_ok": bool(st_ok)}
 if rank == 0:
     pipe1, bp1 = run([1000 + i for i in range(nsim)])
     N1, S1, C1 = pipe1.stats()
