@@ -48,12 +48,13 @@ expand_half_kernel(const T2 *__restrict__ kh, T2 *__restrict__ full, const doubl
     re[c] = (double)z.x * scale;
     im[c] = (mirror ? -(double)z.y : (double)z.y) * scale;
   }
-  if (ROT && NC == 3) {
+  if (ROT && NC >= 2) {   // the LAST two components, as maps.py:1615 rotates emap[...,-2:,:,:] (ncomp 2: Q,U; 3: I,Q,U)
+    constexpr int A = NC >= 2 ? NC - 2 : 0, B = NC >= 2 ? NC - 1 : 0;
     double c, s;
     rot_cs(ly[iy], lx[ix], rot_sgn, c, s);
-    double er = c * re[1] - s * re[2], ei = c * im[1] - s * im[2];
-    double br = s * re[1] + c * re[2], bi = s * im[1] + c * im[2];
-    re[1] = er; im[1] = ei; re[2] = br; im[2] = bi;
+    double er = c * re[A] - s * re[B], ei = c * im[A] - s * im[B];
+    double br = s * re[A] + c * re[B], bi = s * im[A] + c * im[B];
+    re[A] = er; im[A] = ei; re[B] = br; im[B] = bi;
   }
 #pragma unroll
   for (int c = 0; c < NC; c++) {
@@ -141,7 +142,7 @@ int launch_expand(const void *kh, void *full, ox_geometry *g, int nbatch, double
   long long n = (long long)g->ny * g->nx;
   dim3 grid((unsigned)((n + PW_THREADS - 1) / PW_THREADS), nbatch);
   double sgn = (flags & OX_FLAG_IAU) ? 1.0 : -1.0;
-  if ((flags & OX_FLAG_ROT) && NC == 3)
+  if ((flags & OX_FLAG_ROT) && NC >= 2)
     expand_half_kernel<T2, NC, true><<<grid, PW_THREADS, 0, g_stream>>>((const T2 *)kh, (T2 *)full, g->ly.as<double>(),
                                                                        g->lx.as<double>(), g->ny, g->nx, g->nxh, scale, sgn);
   else

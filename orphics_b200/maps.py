@@ -346,7 +346,7 @@ class FourierCalc(object):
             raise ValueError(f"normalize={normalize!r}")
         a, loc, nc, _keep = self._as_stack(emap)
         out, optr, oloc = result_map(np.shape(emap), _capi.np_cdtype(self.dtype), self.wcs)
-        flags = self._flags(rot=rot and nc == 3, normalize=bool(normalize))
+        flags = self._flags(rot=rot and nc >= 2, normalize=bool(normalize))     # (the last two components, maps.py:1615)
         check(lib.ox_power_fft(self._plan(nc), a, loc, 1, flags, optr, oloc))
         if phys:
             # enmap.fft(normalize="phys") = the unitary transform x pixsize^1/2 (lensing.py:403, 653)
@@ -434,7 +434,7 @@ class FourierCalc(object):
         k2, k2ptr = k1, None
         if a2 is not None:
             k2, k2ptr, _ = result_map(kshape, cdt, wcs)
-        flags = self._flags(rot=rot and nc == 3, pixel_units=pixel_units, skip_cross=skip_cross)
+        flags = self._flags(rot=rot and nc >= 2, pixel_units=pixel_units, skip_cross=skip_cross)
         check(lib.ox_power2d(self._plan(nc), a1, a2, loc1, 1, flags, pptr, k1ptr, k2ptr, oloc))
         if multi:
             # the reference returns a plain (ncomp,ncomp,Ny,Nx) array here (np.zeros, maps.py:1662)
@@ -470,6 +470,8 @@ class FourierCalc(object):
         wp, wloc, _kw = (None, OX_HOST, None) if window is None else _dev_in(window, rdt)
         ns = nc if (skip_cross and nc > 1) else nc * (nc + 1) // 2
         out = np.empty((nb, ns, binner.centers.size), dtype=np.float64)
+        if rot and nc == 2:
+            raise NotImplementedError("binned_power_batch: the fused power+bin kernel rotates (I,Q,U) stacks only; use power2d + bin for (Q,U)")
         flags = self._flags(rot=rot and nc == 3, pixel_units=pixel_units, skip_cross=skip_cross)
         check(lib.ox_power_bin(self._plan(nc, nb), binner.handle, a1, a2, loc, nb, flags, wp, wloc, ptr(out), OX_HOST))
         # bin2D's short-bincount quirk (stats.py:796-797): same length as binner.bin() returns

@@ -496,3 +496,12 @@ def test_reference_options_real_noise_phys_normalisation_complex_filter(pol, the
     got = maps.filter_map(maps.ndmap(np.asarray(m), wcs), kf)
     assert got.dtype == np.float64 and relerr(got, omaps.filter_map(m, kf)) < TOL64
     assert relerr(maps.filter_map(maps.ndmap(np.asarray(m), wcs), kf.real + 0j), omaps.filter_map(m, kf.real)) < TOL64
+    if pol:
+        # a (Q,U) pair on its own: the reference rotates the LAST two components whatever their number (maps.py:1615)
+        qu = np.asarray(m)[1:]
+        fc2, ofc2 = maps.FourierCalc((2,) + tuple(shape[-2:]), wcs), omaps.FourierCalc((2,) + tuple(so[-2:]), wo)
+        assert relerr(fc2.iqu2teb(maps.ndmap(qu, wcs), normalize=False), ofc2.iqu2teb(oenmap.ndmap(qu, wo), normalize=False)) < TOL64
+        p2, k2, _ = fc2.power2d(maps.ndmap(qu, wcs))
+        op2, ok2, _ = ofc2.power2d(oenmap.ndmap(qu, wo))
+        assert np.shape(p2) == (2, 2) + tuple(shape[-2:]) and relerr(p2, op2) < TOL64 and relerr(k2, ok2) < TOL64
+        assert relerr(p2[0, 0], fc.power2d(maps.ndmap(np.asarray(m), wcs))[0][1, 1]) < TOL64       # EE from (Q,U) == EE from (I,Q,U)
