@@ -135,6 +135,7 @@ struct RowArgs {
   // once per launch instead of once per plane (ncu round 1: 66 MB read per 33.5 MB map with rows fastest);
   // 0 = rows fastest, blockIdx.y = plane (ORPHX_KB_ORDER=rows)
   int nplanes_fast = 0;
+  int tile_order = 0;   // persistent TMA row pass only: how its tiles are dealt to the CTAs (ox_row_tma.cuh tile_coords)
   // separable window (full pass only): window[iy][ix] = fl(win_y[iy] * win_x[ix]) exactly, e.g. the reference's
   // cosine taper (maps.py:1893-1920).  The row kernel then reads the 8*nx-byte x profile (L1-resident) and one
   // scalar per row instead of streaming the 8*ny*nx-byte window through L2 for every plane.

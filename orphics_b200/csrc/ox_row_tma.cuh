@@ -131,19 +131,35 @@ struct RowTmaStore {
   }
 };
 
-// tile number -> (row tile, plane).  nplanes_fast > 0: planes vary fastest (CTAs resident together share the rows of a
-// batch-shared 2-D window); nplanes_fast < 0: rows vary fastest inside a plane (-nplanes_fast = row tiles per plane): the
-// 64-byte segments that neighbouring row tiles read and write in one DRAM page are touched together.
+// The i-th tile of CTA blockIdx.x -> (row tile, plane); false past the CTA's last tile.
+//   tile_order 2 (default): PAIRS of adjacent row tiles of one plane go to one CTA as consecutive tiles (2q, 2q+1) -- its two
+//     groups work on them at the same time.  The 64-byte segments of two adjacent 4-row tiles are the two halves of one
+//     128-byte line; the TMA unit reads whole lines from L2 for a 64-byte box row (ncu: 125 M sectors for 67 M of data), so
+//     with the halves requested microseconds apart by one SM the second request hits L2 and the DRAM traffic is the data,
+//     once (it was 1.01-1.13 x the data depending on timing when the neighbour tile belonged to another CTA).  Pairs are dealt
+//     to the CTAs planes-fastest, so a 2-D window shared by the planes is still read from DRAM once per launch.
+//   tile_order 0: single tiles, planes fastest;  1: single tiles, rows fastest inside a plane.
 template <typename T>
-__device__ __forceinline__ void tile_coords(const RowArgs<T> &a, int t, int nplanes, int &rowtile, int &plane) {
-  if (a.nplanes_fast < 0) {
-    const int per = -a.nplanes_fast;
+__device__ __forceinline__ bool tile_coords(const RowArgs<T> &a, int i, int nplanes, int ntiles, int &rowtile, int &plane) {
+  if (a.tile_order == 2) {
+    const int pair = blockIdx.x + (i >> 1) * gridDim.x;
+    if (2 * pair >= ntiles) return false;
+    const int rp = pair / nplanes;
+    plane = pair - rp * nplanes;
+    rowtile = 2 * rp + (i & 1);
+    return true;
+  }
+  const int t = blockIdx.x + i * gridDim.x;   // (ntiles + gridDim.x < 2^31, checked by the launcher)
+  if (t >= ntiles) return false;
+  if (a.tile_order == 1) {
+    const int per = ntiles / nplanes;
     plane = t / per;
     rowtile = t - plane * per;
   } else {
     rowtile = t / nplanes;
     plane = t - rowtile * nplanes;
   }
+  return true;
 }
 
 template <int MX, int R>
@@ -182,10 +198,8 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
   extern __shared__ unsigned char smem_dyn[];
   // one thread: fetch the i-th tile of this CTA into slot i % 3 (nothing to do past the CTA's last tile)
   auto issue = [&a, &tmap, nplanes, ntiles](unsigned char *base, int i) {
-    const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
-    if (t >= ntiles) return;
     int rowtile, plane;
-    tile_coords(a, (int)t, nplanes, rowtile, plane);
+    if (!tile_coords(a, i, nplanes, ntiles, rowtile, plane)) return;
     const int slot = i % 3;
     unsigned char *dst = base + slot * Cfg::SLOT;
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot;
@@ -242,8 +256,8 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     const int f = gt / NT, u = gt - f * NT;
     const int grp_bar = 1 + g, row_bar = 3 + g * R + f;
     __builtin_assume(row_bar > 0);   // (the engine's barrier 0 = __syncthreads is never used here)
-    const int t = blockIdx.x + i * gridDim.x;   // (ntiles + gridDim.x < 2^31, checked by the launcher)
-    if (t >= ntiles) break;
+    int rowtile, plane_i;
+    if (!tile_coords(a, i, nplanes, ntiles, rowtile, plane_i)) break;
     unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
     const int slot = i % 3;
     T2 *s = reinterpret_cast<T2 *>(base + slot * Cfg::SLOT);
@@ -259,8 +273,6 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     } else {
       tws.init(a.tw, a.tw_len / MX, u);
     }
-    int rowtile, plane_i;
-    tile_coords(a, t, nplanes, rowtile, plane_i);
     const long long plane = plane_i;
     T2 keep[16];
     {
@@ -350,10 +362,11 @@ inline bool row_tma_enabled() {
   return !(e && !strcmp(e, "legacy"));
 }
 
-inline bool row_tma_rows_fastest(bool dflt) {
+inline int row_tma_tile_order(int dflt) {   // ORPHX_KB_TILE_ORDER = pairs | planes | rows (see tile_coords)
   const char *e = getenv("ORPHX_KB_TILE_ORDER");
-  if (e && !strcmp(e, "rows")) return true;
-  if (e && !strcmp(e, "planes")) return false;
+  if (e && !strcmp(e, "pairs")) return 2;   // (the launcher only offers it for an even number of row tiles)
+  if (e && !strcmp(e, "planes")) return 0;
+  if (e && !strcmp(e, "rows")) return 1;
   return dflt;
 }
 inline CUtensorMapL2promotion row_tma_l2_promotion() {
@@ -395,9 +408,11 @@ int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
       OX_TRY(set_smem(k, SMEM));
       int grid = sm_count();   // one persistent CTA per SM
       if ((long long)grid * 2 > ntiles) grid = (int)((ntiles + 1) / 2);
-      // planes fastest: a 2-D window shared by the planes is read from DRAM once per launch (ORPHX_KB_TILE_ORDER=rows: rows
-      // fastest inside a plane)
-      a.nplanes_fast = row_tma_rows_fastest(false) ? -(a.ny / R) : (int)nplanes;   // (measured: no difference, profiles/r02_variants.txt)
+      // (with a general 2-D window streamed from L2 the paired order measured 9% slower than single tiles: 2.29 vs 2.10 ms)
+      const bool general_window = a.window != nullptr && a.win_x == nullptr;
+      a.tile_order = row_tma_tile_order((a.ny / R) % 2 == 0 && !general_window ? 2 : 0);
+      if ((a.ny / R) % 2 != 0 && a.tile_order == 2) a.tile_order = 0;
+      a.nplanes_fast = (int)nplanes;
       k<<<grid, Cfg::NTHREADS, SMEM, g_stream>>>(a, tmap, (int)nplanes, (int)ntiles);
       OX_KERNEL_CHECK();
       *launched = true;

@@ -98,7 +98,9 @@ if traffic:
 steps = (("prof_r02d.ncu-rep", "fused_row_kernel", "one tile per CTA, LDGSTS tile loads (round 1 kernel + planes-fastest order + separable window)"),
          ("prof_r02c.ncu-rep", "fused_row_tma", "persistent TMA kernel, first version (slot bookkeeping in shared memory, tables through L1)"),
          ("prof_r02e.ncu-rep", "fused_row_tma", "static schedule + window profile / twiddles in shared memory"),
-         ("prof_r02g.ncu-rep", "fused_row_tma", "+ parity-split twiddle table, compact second-stage table, flat-window skip (final)"),
+         ("prof_r02g.ncu-rep", "fused_row_tma", "+ parity-split twiddle table, compact second-stage table, flat-window skip"),
+         ("prof_r02_planes.ncu-rep", "fused_row_tma", "same kernel, single tiles dealt planes-fastest, captured in the session of the next entry"),
+         ("prof_r02_pairs.ncu-rep", "fused_row_tma", "+ PAIRS of adjacent row tiles per CTA (the two 64 B halves of a 128 B line meet in L2): final"),
          ("prof_r02f.ncu-rep", "fused_row_w32", "experiment: one warp per row, two radix-32 stages (254 registers, 8 warps/SM) -- rejected"))
 out = ["ncu --set full --clock-control none -k regex:<row kernel> --launch-skip 3 --launch-count 1 : python bench.py --steps 1 --warmup 3 --no-e2e "
        "--cpu-sample 0 --batch 64 --no-extras --configs none", "(64 maps of 2048^2 fp64 per launch; algorithmic bytes 3 s N x 64 = 6.44 GB)", ""]
