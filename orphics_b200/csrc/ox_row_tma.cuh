@@ -132,8 +132,8 @@ struct RowTmaStore {
 };
 
 // The i-th tile of CTA blockIdx.x -> (row tile, plane); false past the CTA's last tile.
-//   tile_order 2 (default): PAIRS of adjacent row tiles of one plane go to one CTA as consecutive tiles (2q, 2q+1) -- its two
-//     groups work on them at the same time.  The 64-byte segments of two adjacent 4-row tiles are the two halves of one
+//   tile_order G >= 2 (default: G = 8 / R, the row tiles that share a 128-byte line): BLOCKS of G adjacent row tiles of one plane
+//     go to one CTA as consecutive tiles -- for 4-row tiles a pair (2q, 2q+1) that its two groups work on at the same time.  The 64-byte segments of two adjacent 4-row tiles are the two halves of one
 //     128-byte line; the TMA unit reads whole lines from L2 for a 64-byte box row (ncu: 125 M sectors for 67 M of data), so
 //     with the halves requested microseconds apart by one SM the second request hits L2 and the DRAM traffic is the data,
 //     once (it was 1.01-1.13 x the data depending on timing when the neighbour tile belonged to another CTA).  Pairs are dealt
@@ -141,12 +141,13 @@ struct RowTmaStore {
 //   tile_order 0: single tiles, planes fastest;  1: single tiles, rows fastest inside a plane.
 template <typename T>
 __device__ __forceinline__ bool tile_coords(const RowArgs<T> &a, int i, int nplanes, int ntiles, int &rowtile, int &plane) {
-  if (a.tile_order == 2) {
-    const int pair = blockIdx.x + (i >> 1) * gridDim.x;
-    if (2 * pair >= ntiles) return false;
-    const int rp = pair / nplanes;
-    plane = pair - rp * nplanes;
-    rowtile = 2 * rp + (i & 1);
+  if (a.tile_order >= 2) {   // blocks of tile_order adjacent row tiles (2 for 4-row tiles, 4 for 2-row tiles: one 128-byte line)
+    const int G = a.tile_order;
+    const int blk = blockIdx.x + (i / G) * gridDim.x;
+    if (G * blk >= ntiles) return false;
+    const int rp = blk / nplanes;
+    plane = blk - rp * nplanes;
+    rowtile = G * rp + (i % G);
     return true;
   }
   const int t = blockIdx.x + i * gridDim.x;   // (ntiles + gridDim.x < 2^31, checked by the launcher)
@@ -210,15 +211,20 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
       tma_load_3d(dst + (size_t)j * Cfg::BOXW * R * 16, &tmap, 2 * rowtile * R, j * Cfg::BOXW, plane, bar);
     const T2 *nyq = a.Hin + ((long long)plane * (MX + 1) + MX) * a.ny + rowtile * R;
     bulk_load(dst + (size_t)MX * R * 16, nyq, R * 16, bar);
+    __threadfence_block();
+    reinterpret_cast<volatile int *>(base + 3 * Cfg::SLOT + 40)[slot] = i / 3 + 1;   // fills issued into this slot so far
   };
 
   {
-    // slots aligned to 1024 B; [3 slots][3 mbarriers + flat-block mask (64 B)][twiddles, split by parity][16 second-stage
+    // slots aligned to 1024 B; [3 slots][3 mbarriers, flat-block mask, 3 fill counters (64 B)][twiddles, split by parity][16 second-stage
     // twiddles][x profile of the window]
     unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
     if (threadIdx.x == 0) {
       unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT);
-      for (int b = 0; b < 3; b++) mbar_init(bars + b, 1);
+      for (int b = 0; b < 3; b++) {
+        mbar_init(bars + b, 1);
+        reinterpret_cast<volatile int *>(base + 3 * Cfg::SLOT + 40)[b] = 0;
+      }
       fence_mbar_init();
       issue(base, 0);
       issue(base, 1);
@@ -296,7 +302,21 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
       }
       T2 wu = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64)[FFT::SmemTwiddles::tpos(u)];   // (u < MX/16: inside the table)
       wu.y = -wu.y;  // e^{+2 pi i u/Nx}
-      mbar_wait(reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot, (unsigned)((i / 3) & 1));  // the tile has landed
+      // The tile has landed.  mbarrier waits name a phase by its PARITY only, so the wait for fill k must not start while
+      // the slot's barrier is still in phase k-1 (it would be taken for the completed phase k-2 and the group would read
+      // the previous tile): that can happen when this group runs a tile and a half ahead of the other one while the TMA
+      // unit is backed up -- the load of tile i-3, issued by this group two tiles ago and to be consumed by the other
+      // group, has not landed yet (seen with 2-row tiles, whose 32-byte box rows make the TMA unit the bottleneck).  The
+      // issuing thread therefore publishes the number of fills issued per slot, and a waiter first sees fill k issued
+      // (true long before in the normal case: one shared-memory load), which puts the barrier in phase k or past it.
+      {
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot;
+        const int k = i / 3;
+        const volatile int *fills = reinterpret_cast<const volatile int *>(base + 3 * Cfg::SLOT + 40);
+        while (fills[slot] <= k) {}          // fill k has been issued: the barrier is in phase k (or past it)
+        __threadfence_block();
+        mbar_wait(bar, (unsigned)(k & 1));
+      }
       PackLoadTile<T2, MX, R> ld{s, f, wu};
       // first-stage reads come from the tile (all rows interleaved) -> group-wide barrier before the writes
       FFT::template run<+1, true, false>(row, tws, u, row_bar, ld, wst, grp_bar, GROUP);
@@ -362,6 +382,11 @@ inline bool row_tma_enabled() {
   return !(e && !strcmp(e, "legacy"));
 }
 
+// 2-row tiles (nx = 4096: the estimator's c2r pass at 4096^2, 1.72 -> 1.42 ms per 8 realisations): ORPHX_KB_R2 = 0 turns them off
+inline bool row_tma_r2_enabled() {
+  const char *e = getenv("ORPHX_KB_R2");
+  return !(e && e[0] == '0');
+}
 inline int row_tma_tile_order(int dflt) {   // ORPHX_KB_TILE_ORDER = pairs | planes | rows (see tile_coords)
   const char *e = getenv("ORPHX_KB_TILE_ORDER");
   if (e && !strcmp(e, "pairs")) return 2;   // (the launcher only offers it for an even number of row tiles)
@@ -384,9 +409,10 @@ int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
     constexpr int R = RowCfg<T, MX>::R;
     typedef RowTmaCfg<MX, R> Cfg;
     constexpr size_t SMEM = (MODE & ROW_OUT_H) ? Cfg::SMEM_FULL : Cfg::SMEM_C2R;
-    // (R = 2, the 32-byte segments of nx = 4096 in 70 KB slots, measured slower than the one-tile kernel: 2.05 vs
-    // 1.72 ms for the estimator's c2r pass -- the TMA unit is fed 32 B box rows)
-    if constexpr (SMEM <= SMEM_MAX && Cfg::NTHREADS <= 1024 && R == 4) {
+    // (R = 2, the 32-byte segments of nx = 4096 in 70 KB slots: with single tiles per CTA it measured 2.05 ms against 1.72 ms
+    // for the one-tile kernel on the estimator's c2r pass; with blocks of four adjacent row tiles per CTA 1.42 ms)
+    if constexpr (SMEM <= SMEM_MAX && Cfg::NTHREADS <= 1024 && (R == 4 || R == 2)) {
+      if (R == 2 && !row_tma_r2_enabled()) return OX_OK;
       if (!row_tma_enabled() || !tma_encoder() || a.ny % R != 0) return OX_OK;
       const long long ntiles = (long long)(a.ny / R) * nplanes;
       if (ntiles >= (1LL << 30) || nplanes >= (1LL << 30)) return OX_OK;
@@ -410,8 +436,10 @@ int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
       if ((long long)grid * 2 > ntiles) grid = (int)((ntiles + 1) / 2);
       // (with a general 2-D window streamed from L2 the paired order measured 9% slower than single tiles: 2.29 vs 2.10 ms)
       const bool general_window = a.window != nullptr && a.win_x == nullptr;
-      a.tile_order = row_tma_tile_order((a.ny / R) % 2 == 0 && !general_window ? 2 : 0);
-      if ((a.ny / R) % 2 != 0 && a.tile_order == 2) a.tile_order = 0;
+      constexpr int G = 8 / R;   // row tiles per 128-byte line
+      a.tile_order = row_tma_tile_order((a.ny / R) % G == 0 && !general_window ? G : 0);
+      if ((a.ny / R) % G != 0 && a.tile_order >= 2) a.tile_order = 0;
+      if (a.tile_order >= 2) a.tile_order = G;
       a.nplanes_fast = (int)nplanes;
       k<<<grid, Cfg::NTHREADS, SMEM, g_stream>>>(a, tmap, (int)nplanes, (int)ntiles);
       OX_KERNEL_CHECK();

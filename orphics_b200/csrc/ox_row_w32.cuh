@@ -119,13 +119,18 @@ fused_row_w32_kernel(RowArgs<double> a, const __grid_constant__ CUtensorMap tmap
       tma_load_3d(dst + (size_t)j * Cfg::BOXW * R * 16, &tmap, 2 * rowtile * R, j * Cfg::BOXW, plane, bar);
     const T2 *nyq = a.Hin + ((long long)plane * (MX + 1) + MX) * a.ny + rowtile * R;
     bulk_load(dst + (size_t)MX * R * 16, nyq, R * 16, bar);
+    __threadfence_block();
+    reinterpret_cast<volatile int *>(base + 3 * Cfg::SLOT + 40)[slot] = i / 3 + 1;   // fills issued into this slot so far
   };
 
   {
     unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
     if (threadIdx.x == 0) {
       unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT);
-      for (int b = 0; b < 3; b++) mbar_init(bars + b, 1);
+      for (int b = 0; b < 3; b++) {
+        mbar_init(bars + b, 1);
+        reinterpret_cast<volatile int *>(base + 3 * Cfg::SLOT + 40)[b] = 0;
+      }
       fence_mbar_init();
       issue(base, 0);
       issue(base, 1);
@@ -164,7 +169,14 @@ fused_row_w32_kernel(RowArgs<double> a, const __grid_constant__ CUtensorMap tmap
       constexpr double C[32] = OX_C64, S[32] = OX_S64;
       T2 wu = utw[j];
       wu.y = -wu.y;
-      mbar_wait(reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot, (unsigned)((i / 3) & 1));  // the tile has landed
+      {   // the tile has landed (fill k-1 first: see ox_row_tma.cuh)
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot;
+        const int k = i / 3;
+        const volatile int *fills = reinterpret_cast<const volatile int *>(base + 3 * Cfg::SLOT + 40);
+        while (fills[slot] <= k) {}          // fill k has been issued: the barrier is in phase k (or past it)
+        __threadfence_block();
+        mbar_wait(bar, (unsigned)(k & 1));
+      }
 #pragma unroll
       for (int m = 0; m < 32; m++) {
         const int k = j + 32 * m;

@@ -269,6 +269,28 @@ def test_flat_lensing_sims_match_oracle(pol, theory):
     assert relerr(bobs, got[5]) < 5e-2
 
 
+def test_tma_c2r_pass_of_the_estimator_matches_the_one_tile_kernel(monkeypatch):
+    """The estimator's c2r row pass at nx = 4096 runs on the persistent TMA kernel with 2-row tiles (ox_row_tma.cuh).  On
+    512 x 4096 x 8 realisations (41 tiles per CTA) the first version returned sporadic wrong realisations: a group that ran
+    ahead took a slot's still-pending previous fill for its own (mbarrier waits only know a phase's parity); the per-slot
+    fill counters make that impossible.  Same bits as the one-tile kernel, several repetitions."""
+    from orphics_b200 import maps, lensing, cosmology
+    ny, nx, nb = 512, 4096, 8
+    shape, wcs = maps.rect_geometry(width_arcmin=nx * 0.5, px_res_arcmin=0.5, height_arcmin=ny * 0.5)
+    assert tuple(shape) == (ny, nx)
+    modl = maps.Geometry.get(shape, wcs).modlmap()
+    q = lensing.qest(shape, wcs, cosmology.default_theory(), noise2d=np.zeros(shape) + (1.0 * np.pi / 180 / 60) ** 2,
+                     beam2d=maps.gauss_beam(modl, 1.5), kmask=maps.mask_kspace(shape, wcs, lmin=300, lmax=2000),
+                     kmask_K=maps.mask_kspace(shape, wcs, lmin=20, lmax=3500), unlensed_equals_lensed=True, max_batch=nb)
+    assert q.path("TT") == "fused"
+    T = np.random.RandomState(1).standard_normal((nb,) + tuple(shape)) * 50
+    monkeypatch.setenv("ORPHX_KB", "legacy")
+    want = np.asarray(q.kappa_from_maps("TT", T, returnFt=True))
+    monkeypatch.setenv("ORPHX_KB", "tma")
+    for _ in range(4):
+        assert np.array_equal(np.asarray(q.kappa_from_maps("TT", T, returnFt=True)), want)
+
+
 def test_hermitian_check_is_exhaustive(theory):
     """A k-map that is Hermitian everywhere except in ONE pixel pair (on a row that a sampled check would skip) must
     not take the half-plane path: the result has to be the reference's full-plane chain on that input."""
