@@ -76,7 +76,7 @@ if os.path.exists(T):
         add("T2048_f64", stage, "prof_r02_T.ncu-rep", m, "prof_r02_T: 64 maps per launch")
 txt = []
 for rep, stage, key, m, what in (("prof_r02_IQU.ncu-rep", "K_A sim+col_ifft", "IQU2048_f64", "fused_sim_col_kernel", "configs[2]: 16 IQU realisations per launch"),
-                                 ("prof_r02_TT.ncu-rep", "Q3a rows c2r", "QE_TT4096_f64", "fused_row_kernel", "configs[3]: 8 realisations of 4096^2 per launch"),
+                                 ("prof_r02_TT.ncu-rep", "Q3a rows c2r", "QE_TT4096_f64", "fused_row_tma_kernel", "configs[3]: 8 realisations of 4096^2 per launch"),
                                  ("prof_r02_EB64.ncu-rep", "Q3a rows c2r", "QE_EB8192_f64", "fused_row_kernel", "configs[4] fp64: 2 realisations of 8192^2 per launch"),
                                  ("prof_r02_EB32.ncu-rep", "Q2b legs cols inv", "QE_EB8192_f32", "fused_col_kernel", "configs[4] fp32: 2 realisations of 8192^2 per launch")):
     add(key, stage, rep, m, what)
