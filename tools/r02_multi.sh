@@ -1,13 +1,13 @@
 #!/bin/bash
 # round-2 multi-GPU call: tools/r02_multi.sh N  -- the 2-rank NCCL test (N >= 2), the bench at N ranks (weak, with the configs block:
-# IQU, strong-scaled TT estimator + mean-field all-reduce, EB 8192^2), and the reference arm on rank 0
+# IQU, strong-scaled TT estimator + mean-field all-reduce, EB 8192^2).  Bounded steps.
 N=${1:-2}
 mkdir -p gpurun_out
 if [ "$N" = "2" ]; then
-  ( time timeout 900 python -m pytest tests/test_gpu_dist.py -m gpu -x -q ) > gpurun_out/r02_tests_n2.log 2>&1
+  ( time timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -x -q ) > gpurun_out/r02_tests_n2.log 2>&1
   tail -5 gpurun_out/r02_tests_n2.log
 fi
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 64 --warmup 3 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 64 --warmup 3 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
 python - <<PY
 import json
 try:
