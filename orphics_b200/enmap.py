@@ -126,10 +126,11 @@ class devmap(object):
         return cls(buf, buf.ptr, shape, dtype, wcs)
 
     @classmethod
-    def from_host(cls, arr, wcs=None):
-        """Both copies valid: the array is uploaded now and kept as the host view."""
+    def from_host(cls, arr, wcs=None, copy=True):
+        """Both copies valid: the array is uploaded now and a private copy (copy=False: the array itself, for arrays
+        the caller hands over) is kept as the host view -- later edits of the caller's array must not reach one copy only."""
         wcs = getattr(arr, "wcs", None) if wcs is None else wcs
-        a = np.ascontiguousarray(arr)
+        a = np.array(arr, copy=True, order="C") if copy else np.ascontiguousarray(arr)
         out = cls.empty(a.shape, a.dtype, wcs)
         check(lib.ox_memcpy_h2d(C.c_void_p(out._ptr), ptr(a), a.nbytes))
         out._host = ndmap(a, wcs)
@@ -266,7 +267,7 @@ class devmap(object):
         if len(oshape) > self.ndim or oshape != self.shape[self.ndim - len(oshape):] or not oshape:
             return NotImplemented
         if b is None:
-            b = devmap.from_host(other)
+            b = devmap.from_host(other, copy=False)      # (a temporary for this one operation)
         out = devmap.empty(self.shape, self.dtype, self.wcs if self.wcs is not None else getattr(other, "wcs", None))
         check(lib.ox_map_op(_OPS[op], C.c_void_p(self.ptr), C.c_void_p(b.ptr), C.c_double(0.0), self.size, b.size, kind,
                             C.c_void_p(out._ptr)))
@@ -299,10 +300,17 @@ class devmap(object):
                 r = b._device_op(_REFLECT[op], a)
             if r is not NotImplemented:
                 return r
-        if "out" in kwargs:
-            kwargs["out"] = tuple(o.host() if isinstance(o, devmap) else o for o in kwargs["out"])
+        outs = kwargs.get("out", ())
+        if outs:
+            kwargs["out"] = tuple(o.host() if isinstance(o, devmap) else o for o in outs)
         args = [x.host() if isinstance(x, devmap) else x for x in inputs]
-        return getattr(ufunc, method)(*args, **kwargs)
+        res = getattr(ufunc, method)(*args, **kwargs)
+        for o in outs:
+            if isinstance(o, devmap):     # written on the host: the device copy is stale now
+                o._dev_valid = False
+                if o._owner is not None and o._ptr != o._owner.ptr:
+                    o._owner = None
+        return res
 
 
 def _host_fallback(name):
@@ -325,7 +333,8 @@ def to_device(x, dtype=None, wcs=None):
     if isinstance(x, devmap) and (dtype is None or x.dtype == np.dtype(dtype)):
         return x
     a = np.asarray(x) if dtype is None else np.asarray(x, dtype=dtype)
-    return devmap.from_host(a, getattr(x, "wcs", None) if wcs is None else wcs)
+    aliases = isinstance(x, np.ndarray) and np.shares_memory(a, x)      # (a fresh conversion needs no second copy)
+    return devmap.from_host(a, getattr(x, "wcs", None) if wcs is None else wcs, copy=aliases)
 
 
 def result_map(shape, dtype, wcs):

@@ -538,7 +538,7 @@ def get_taper(shape, wcs, taper_percent=12.0, pad_percent=3.0, weight=None):
     w2 = np.mean(taper ** 2.)
     if enmap.DEVICE_RESIDENT:
         # host and device copies: `imap * taper` with a device-resident imap stays on the device
-        return devmap.from_host(taper, wcs), w2
+        return devmap.from_host(taper, wcs, copy=False), w2
     return ndmap(taper, wcs), w2
 
 

@@ -84,6 +84,15 @@ def test_devmap_behaves_as_the_ndmap_it_stands_for(setup):
     h2[0, :] = 7.0
     assert np.array_equal(np.asarray(m2 * wd), h2 * w)
     assert np.array_equal(np.asarray(m), h)                               # the original is untouched
+    # a ufunc writing INTO a devmap runs on the host copy; the device copy follows on next use
+    m3 = m.copy()
+    np.multiply(h, 3.0, out=m3)
+    assert np.array_equal(np.asarray(m3 * wd), (h * 3.0) * w)
+    # from_host keeps a private copy: editing the caller's array afterwards reaches neither copy
+    w2 = w.copy()
+    d2 = enmap.devmap.from_host(w2)
+    w2[:] = 0.0
+    assert np.array_equal(np.asarray(d2), w) and np.array_equal(np.asarray(m * d2), h * w)
 
 
 def test_component_stacks_and_views(setup):
