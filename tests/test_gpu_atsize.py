@@ -177,3 +177,25 @@ def test_config4_qe_8192_spot_check(theory):
     assert relerr(q.kappa_from_map("TT", T, returnFt=True), qo.kappa_from_map("TT", T, returnFt=True)) < TOL64
     E, B = T * 0.07, _observed_like(shape, rng, 1.0)
     assert relerr(q.kappa_from_map("EB", None, E, B, returnFt=True), qo.kappa_from_map("EB", None, E, B, returnFt=True)) < TOL64
+
+
+def test_tma_row_pass_stress_at_2048(monkeypatch):
+    """256 maps of 2048^2 (four launches of 64: 221 tiles per CTA and launch, the benchmark's shape) through the persistent TMA row
+    pass and through the one-tile kernel on the same Philox seeds: every bandpower of every map agrees to rounding (a single
+    misread tile -- what a phase mix-up of the slot barriers produces -- moves a bandpower by ~1e-3)."""
+    from orphics_b200 import maps, stats, cosmology
+    shape, wcs = maps.rect_geometry(width_arcmin=2048 * 0.5, px_res_arcmin=0.5)
+    g = maps.Geometry.get(shape, wcs)
+    ps = cosmology.power_from_theory(np.arange(0, g.modlmap().max() + 1, 1.0), cosmology.default_theory(), lensed=True, pol=False)
+    taper = np.asarray(maps.get_taper(shape, wcs)[0])
+    out = {}
+    for kb in ("legacy", "tma"):
+        monkeypatch.setenv("ORPHX_KB", kb)
+        mg = maps.MapGen(shape, wcs, ps, noise="philox_hermitian", max_batch=64)
+        fc = maps.FourierCalc(shape, wcs, max_batch=64)
+        b = stats.bin2D(g.modlmap(), EDGES, geometry=g)
+        pipe = maps.SimPipeline(mg, fc, b, window=taper)
+        out[kb] = pipe.run(range(5000, 5256), keep_maps=True)
+        del pipe, mg, fc, b
+    rel = np.abs(out["tma"] - out["legacy"]) / np.abs(out["legacy"])
+    assert np.nanmax(rel) < 1e-12
