@@ -163,22 +163,28 @@ __device__ __forceinline__ bool tile_coords(const RowArgs<T> &a, int i, int npla
   return true;
 }
 
-template <int MX, int R>
+// NG groups of R x MX/16 threads over NS = NG + spare shared-memory slots.  Default: 2 groups of 4-row tiles over 3 slots
+// (2-row tiles where 4 rows do not fit: the estimator's c2r pass at nx = 4096).
+template <int MX, int R, int NG = 2, int NS = 3>
 struct RowTmaCfg {
-  static constexpr int NT = MX / 16, GROUP = R * NT, NTHREADS = 2 * GROUP;
+  static constexpr int NT = MX / 16, GROUP = R * NT, NTHREADS = NG * GROUP, NGROUPS = NG, NSLOTS = NS;
   // per-row work area of the FFT engine: pad(MX) + the Nyquist element, rounded up to 2 (mod 8) elements so that
   // equal indices of neighbouring rows fall into different 16-byte bank groups (tighter than padded_size())
   static constexpr int PS0 = MX + MX / 16 + 1, PS = PS0 + ((2 - PS0 % 8) + 8) % 8;
   static constexpr size_t WORK = 16 * (size_t)R * PS;                      // padded work area
   static constexpr size_t TILE = 16 * (size_t)R * (MX + 1);               // raw tile
-  static constexpr size_t SLOT = (((WORK > TILE ? WORK : TILE) + 511) / 512) * 512;  // (the swizzle pattern repeats every 512 B)
+  static constexpr size_t SALIGN = R == 4 ? 512 : 256;                    // (the swizzle pattern repeats every 512 / 256 B)
+  static constexpr size_t SLOT = (((WORK > TILE ? WORK : TILE) + SALIGN - 1) / SALIGN) * SALIGN;
+  static constexpr size_t HDR = 128;                                      // mbarriers [0,64), flat-block mask [64,68), fill counters [68,100)
   static constexpr size_t WINX = 8 * (size_t)(2 * MX);                    // x profile of a separable window
   static constexpr size_t UTW = 16 * (size_t)(MX / 4 + 1);                // exp(-2 pi i k / Nx), k <= Nx/8
   static constexpr size_t TW16 = 16 * 16;                                 // compact copy of the 16 second-stage twiddles
-  static constexpr size_t SMEM_C2R = 3 * SLOT + 64 + UTW + TW16 + 1024;   // slots + mbarriers (+ flags) + twiddles (+ alignment slack)
-  static constexpr size_t SMEM_FULL = 3 * SLOT + 64 + UTW + TW16 + WINX + 1024;
+  static constexpr size_t TABS = NS * SLOT;                               // offset of the header behind the slots
+  static constexpr size_t SMEM_C2R = NS * SLOT + HDR + UTW + TW16 + 1024; // (+ alignment slack)
+  static constexpr size_t SMEM_FULL = NS * SLOT + HDR + UTW + TW16 + WINX + 1024;
   static constexpr int BOXW = 256;                                        // columns per TMA box
   static_assert(MX % BOXW == 0, "MX must be a multiple of the TMA box width");
+  static_assert(NS > NG && NS <= 8 && 1 + NG + NG * R <= 16, "slots / named barriers");
 };
 
 // MODE: ROW_IN_H | ROW_OUT_H (full pass; map_out / window are run-time options) or ROW_IN_H | ROW_OUT_MAP (c2r only)
@@ -187,23 +193,23 @@ struct RowTmaCfg {
 // i % 3 and is transformed by group i % 2.  The group that finishes tile i refills its slot with tile i + 3 (which
 // the OTHER group will transform after its tile i + 1) and moves on to tile i + 2, whose load was started a tile
 // and a half earlier.  The k-th fill of a slot completes phase k of the slot's mbarrier.
-template <typename T, int MX, int R, int MODE>
-__global__ void __launch_bounds__(RowTmaCfg<MX, R>::NTHREADS, 1)
+template <typename T, int MX, int R, int MODE, int NG = 2, int NS = 3>
+__global__ void __launch_bounds__(RowTmaCfg<MX, R, NG, NS>::NTHREADS, 1)
 fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int nplanes, int ntiles) {
   static_assert(sizeof(T) == 8, "the TMA row pass is written for 16-byte elements");
   constexpr bool OUT_H = MODE & ROW_OUT_H;
   typedef typename V2<T>::type T2;
   typedef BlockFFT<T, MX> FFT;
-  typedef RowTmaCfg<MX, R> Cfg;
+  typedef RowTmaCfg<MX, R, NG, NS> Cfg;
   constexpr int NT = Cfg::NT, GROUP = Cfg::GROUP, PS = Cfg::PS, NX = 2 * MX;
   extern __shared__ unsigned char smem_dyn[];
   // one thread: fetch the i-th tile of this CTA into slot i % 3 (nothing to do past the CTA's last tile)
   auto issue = [&a, &tmap, nplanes, ntiles](unsigned char *base, int i) {
     int rowtile, plane;
     if (!tile_coords(a, i, nplanes, ntiles, rowtile, plane)) return;
-    const int slot = i % 3;
+    const int slot = i % NS;
     unsigned char *dst = base + slot * Cfg::SLOT;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + Cfg::TABS) + slot;
     fence_proxy_async();   // the slot was last written through the generic proxy (the FFT work area)
     mbar_expect_tx(bar, (unsigned)Cfg::TILE);
 #pragma unroll
@@ -212,7 +218,7 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     const T2 *nyq = a.Hin + ((long long)plane * (MX + 1) + MX) * a.ny + rowtile * R;
     bulk_load(dst + (size_t)MX * R * 16, nyq, R * 16, bar);
     __threadfence_block();
-    reinterpret_cast<volatile int *>(base + 3 * Cfg::SLOT + 40)[slot] = i / 3 + 1;   // fills issued into this slot so far
+    reinterpret_cast<volatile int *>(base + Cfg::TABS + 68)[slot] = i / NS + 1;   // fills issued into this slot so far
   };
 
   {
@@ -220,26 +226,24 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     // twiddles][x profile of the window]
     unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
     if (threadIdx.x == 0) {
-      unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT);
-      for (int b = 0; b < 3; b++) {
+      unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + Cfg::TABS);
+      for (int b = 0; b < NS; b++) {
         mbar_init(bars + b, 1);
-        reinterpret_cast<volatile int *>(base + 3 * Cfg::SLOT + 40)[b] = 0;
+        reinterpret_cast<volatile int *>(base + Cfg::TABS + 68)[b] = 0;
       }
       fence_mbar_init();
-      issue(base, 0);
-      issue(base, 1);
-      issue(base, 2);
+      for (int b = 0; b < NS; b++) issue(base, b);
     }
-    T2 *utw = reinterpret_cast<T2 *>(base + 3 * Cfg::SLOT + 64);
-    T2 *tw16 = reinterpret_cast<T2 *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW);
-    unsigned *flat = reinterpret_cast<unsigned *>(base + 3 * Cfg::SLOT + 32);
+    T2 *utw = reinterpret_cast<T2 *>(base + Cfg::TABS + Cfg::HDR);
+    T2 *tw16 = reinterpret_cast<T2 *>(base + Cfg::TABS + Cfg::HDR + Cfg::UTW);
+    unsigned *flat = reinterpret_cast<unsigned *>(base + Cfg::TABS + 64);
     const int tws_n = a.tw_len / NX;
     for (int e = threadIdx.x; e <= MX / 4; e += Cfg::NTHREADS) utw[FFT::SmemTwiddles::tpos(e)] = a.tw[e * tws_n];
     if (threadIdx.x < 16) tw16[threadIdx.x] = a.tw[threadIdx.x * (NX / 256) * tws_n];
     if (threadIdx.x == 0) *flat = 0u;
     __syncthreads();
     if (OUT_H && a.win_x != nullptr) {
-      double *swx = reinterpret_cast<double *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW + Cfg::TW16);
+      double *swx = reinterpret_cast<double *>(base + Cfg::TABS + Cfg::HDR + Cfg::UTW + Cfg::TW16);
       for (int e = threadIdx.x; e < NX; e += Cfg::NTHREADS) swx[e] = a.win_x[e];
       // bit m of the mask: the x profile is exactly 1 on columns [2 NT m, 2 NT (m+1)) -- the m-th last-stage outputs of
       // every thread; there z * fl(1 * wy) = z * wy needs no profile load (70% of a cosine taper's columns)
@@ -252,7 +256,7 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     __syncthreads();
   }
 
-  for (int i = threadIdx.x / GROUP;; i += 2) {
+  for (int i = threadIdx.x / GROUP;; i += NG) {
     // Everything but i is rebuilt from the thread index every iteration (it passes through an empty asm so that the
     // compiler can neither hoist the dozens of derived addresses out of the loop nor keep them live across the
     // transforms: with the register file full, hoisted invariants came back from local memory inside every transform)
@@ -260,12 +264,12 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     asm volatile("" : "+r"(tid));
     const int g = tid / GROUP, gt = tid - g * GROUP;
     const int f = gt / NT, u = gt - f * NT;
-    const int grp_bar = 1 + g, row_bar = 3 + g * R + f;
+    const int grp_bar = 1 + g, row_bar = 1 + NG + g * R + f;
     __builtin_assume(row_bar > 0);   // (the engine's barrier 0 = __syncthreads is never used here)
     int rowtile, plane_i;
     if (!tile_coords(a, i, nplanes, ntiles, rowtile, plane_i)) break;
     unsigned char *base = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
-    const int slot = i % 3;
+    const int slot = i % NS;
     T2 *s = reinterpret_cast<T2 *>(base + slot * Cfg::SLOT);
     T2 *row = s + f * PS;
     // twiddles: fetched per stage from the shared-memory table where the plan allows it (frees ~20 registers
@@ -273,8 +277,8 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     constexpr bool STW = FFT::SmemTwiddles::OK;
     typename std::conditional<STW, typename FFT::SmemTwiddles, typename FFT::Twiddles>::type tws;
     if constexpr (STW) {
-      tws.tab = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64);
-      tws.tab16 = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW);
+      tws.tab = reinterpret_cast<const T2 *>(base + Cfg::TABS + Cfg::HDR);
+      tws.tab16 = reinterpret_cast<const T2 *>(base + Cfg::TABS + Cfg::HDR + Cfg::UTW);
       tws.u = u;
     } else {
       tws.init(a.tw, a.tw_len / MX, u);
@@ -293,14 +297,14 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
       wst.flat = 0u;
       if (OUT_H) {
         if (a.win_x != nullptr) {
-          wst.swinx = reinterpret_cast<const double2 *>(base + 3 * Cfg::SLOT + 64 + Cfg::UTW + Cfg::TW16);
+          wst.swinx = reinterpret_cast<const double2 *>(base + Cfg::TABS + Cfg::HDR + Cfg::UTW + Cfg::TW16);
           wst.wy = a.win_y[iy0 + f];
-          wst.flat = *reinterpret_cast<const unsigned *>(base + 3 * Cfg::SLOT + 32);
+          wst.flat = *reinterpret_cast<const unsigned *>(base + Cfg::TABS + 64);
         } else if (a.window != nullptr) {
           wst.win_row = reinterpret_cast<const T2 *>(a.window + (plane / a.group) * a.win_group_stride) + rowoff;
         }
       }
-      T2 wu = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64)[FFT::SmemTwiddles::tpos(u)];   // (u < MX/16: inside the table)
+      T2 wu = reinterpret_cast<const T2 *>(base + Cfg::TABS + Cfg::HDR)[FFT::SmemTwiddles::tpos(u)];   // (u < MX/16: inside the table)
       wu.y = -wu.y;  // e^{+2 pi i u/Nx}
       // The tile has landed.  mbarrier waits name a phase by its PARITY only, so the wait for fill k must not start while
       // the slot's barrier is still in phase k-1 (it would be taken for the completed phase k-2 and the group would read
@@ -310,9 +314,9 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
       // issuing thread therefore publishes the number of fills issued per slot, and a waiter first sees fill k issued
       // (true long before in the normal case: one shared-memory load), which puts the barrier in phase k or past it.
       {
-        unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + 3 * Cfg::SLOT) + slot;
-        const int k = i / 3;
-        const volatile int *fills = reinterpret_cast<const volatile int *>(base + 3 * Cfg::SLOT + 40);
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(base + Cfg::TABS) + slot;
+        const int k = i / NS;
+        const volatile int *fills = reinterpret_cast<const volatile int *>(base + Cfg::TABS + 68);
         while (fills[slot] <= k) {}          // fill k has been issued: the barrier is in phase k (or past it)
         __threadfence_block();
         mbar_wait(bar, (unsigned)(k & 1));
@@ -330,7 +334,7 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
       named_sync(grp_bar, GROUP);
       // transposed store with the r2c unpacking fused in (see fused_row_kernel); w_k from the shared-memory table,
       // second octant by symmetry: w_{Nx/4 - j} = (-Im w_j, -Re w_j) (exact: fused_make_twiddles builds it that way)
-      const T2 *utw = reinterpret_cast<const T2 *>(base + 3 * Cfg::SLOT + 64);
+      const T2 *utw = reinterpret_cast<const T2 *>(base + Cfg::TABS + Cfg::HDR);
       T2 *dst = a.Hout + plane * (long long)(MX + 1) * a.ny + rowtile * R;
 #pragma unroll 4
       for (int e = gt; e < (MX / 2 + 1) * R; e += GROUP) {
@@ -355,7 +359,7 @@ fused_row_tma_kernel(RowArgs<T> a, const __grid_constant__ CUtensorMap tmap, int
     }
     // everybody in the group is done with the slot: one thread refills it, nobody waits for that
     named_sync(grp_bar, GROUP);
-    if (gt == 0) issue(base, i + 3);
+    if (gt == 0) issue(base, i + NS);
   }
 }
 
@@ -401,50 +405,64 @@ inline CUtensorMapL2promotion row_tma_l2_promotion() {
        : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
 }
 
+// one configuration (rows per tile, groups, slots) of the persistent TMA row pass
+template <typename T, int MX, int MODE, int R, int NG, int NS>
+int launch_row_tma_cfg(RowArgs<T> &a, long long nplanes, bool *launched) {
+  typedef RowTmaCfg<MX, R, NG, NS> Cfg;
+  constexpr size_t SMEM = (MODE & ROW_OUT_H) ? Cfg::SMEM_FULL : Cfg::SMEM_C2R;
+  if constexpr (SMEM <= SMEM_MAX && Cfg::NTHREADS <= 1024 && (R == 4 || R == 2)) {
+    if (!tma_encoder() || a.ny % R != 0) return OX_OK;
+    const long long ntiles = (long long)(a.ny / R) * nplanes;
+    if (ntiles >= (1LL << 30) || nplanes >= (1LL << 30)) return OX_OK;
+    // the transposed half planes as a 3-D tensor of doubles: [plane][ix = 0..MX][2 * ny]
+    CUtensorMap tmap;
+    cuuint64_t dims[3] = {(cuuint64_t)2 * a.ny, (cuuint64_t)MX + 1, (cuuint64_t)nplanes};
+    cuuint64_t strides[2] = {(cuuint64_t)a.ny * 16, (cuuint64_t)(MX + 1) * a.ny * 16};
+    cuuint32_t box[3] = {2 * R, Cfg::BOXW, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle swz = R == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>((const void *)a.Hin), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, row_tma_l2_promotion(),
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed (%d) for the row pass %d x %d x %lld", (int)r, a.ny, MX, nplanes);
+      return OX_ERR_CUDA;
+    }
+    auto k = fused_row_tma_kernel<T, MX, R, MODE, NG, NS>;
+    OX_TRY(set_smem(k, SMEM));
+    int grid = sm_count();   // one persistent CTA per SM
+    if ((long long)grid * NG > ntiles) grid = (int)((ntiles + NG - 1) / NG);
+    // (with a general 2-D window streamed from L2 the paired order measured 9% slower than single tiles: 2.29 vs 2.10 ms)
+    const bool general_window = a.window != nullptr && a.win_x == nullptr;
+    constexpr int G = 8 / R;   // row tiles per 128-byte line
+    a.tile_order = row_tma_tile_order((a.ny / R) % G == 0 && !general_window ? G : 0);
+    if ((a.ny / R) % G != 0 && a.tile_order >= 2) a.tile_order = 0;
+    if (a.tile_order >= 2) a.tile_order = G;
+    a.nplanes_fast = (int)nplanes;
+    k<<<grid, Cfg::NTHREADS, SMEM, g_stream>>>(a, tmap, (int)nplanes, (int)ntiles);
+    OX_KERNEL_CHECK();
+    *launched = true;
+  }
+  return OX_OK;
+}
+
 // launches the persistent TMA row pass if this (type, size, mode) has one; *launched says whether it did
 template <typename T, int MX, int MODE>
 int launch_row_tma(RowArgs<T> &a, long long nplanes, bool *launched) {
   *launched = false;
   if constexpr (sizeof(T) == 8 && (MODE == (ROW_IN_H | ROW_OUT_H) || MODE == (ROW_IN_H | ROW_OUT_MAP)) && (MX / 16) % 32 == 0) {
+    if (!row_tma_enabled()) return OX_OK;
     constexpr int R = RowCfg<T, MX>::R;
-    typedef RowTmaCfg<MX, R> Cfg;
-    constexpr size_t SMEM = (MODE & ROW_OUT_H) ? Cfg::SMEM_FULL : Cfg::SMEM_C2R;
+    if constexpr (R == 4 && MODE == (ROW_IN_H | ROW_OUT_H)) {
+      // experiment (ORPHX_KB=tma4): FOUR groups of 2-row tiles over six slots -- every scheduler then holds one warp of each group,
+      // i.e. four different phases of the tile, instead of two warps of each of two groups
+      const char *e = getenv("ORPHX_KB");
+      if (e && !strcmp(e, "tma4")) return launch_row_tma_cfg<T, MX, MODE, 2, 4, 6>(a, nplanes, launched);
+    }
     // (R = 2, the 32-byte segments of nx = 4096 in 70 KB slots: with single tiles per CTA it measured 2.05 ms against 1.72 ms
     // for the one-tile kernel on the estimator's c2r pass; with blocks of four adjacent row tiles per CTA 1.42 ms)
-    if constexpr (SMEM <= SMEM_MAX && Cfg::NTHREADS <= 1024 && (R == 4 || R == 2)) {
-      if (R == 2 && !row_tma_r2_enabled()) return OX_OK;
-      if (!row_tma_enabled() || !tma_encoder() || a.ny % R != 0) return OX_OK;
-      const long long ntiles = (long long)(a.ny / R) * nplanes;
-      if (ntiles >= (1LL << 30) || nplanes >= (1LL << 30)) return OX_OK;
-      // the transposed half planes as a 3-D tensor of doubles: [plane][ix = 0..MX][2 * ny]
-      CUtensorMap tmap;
-      cuuint64_t dims[3] = {(cuuint64_t)2 * a.ny, (cuuint64_t)MX + 1, (cuuint64_t)nplanes};
-      cuuint64_t strides[2] = {(cuuint64_t)a.ny * 16, (cuuint64_t)(MX + 1) * a.ny * 16};
-      cuuint32_t box[3] = {2 * R, Cfg::BOXW, 1};
-      cuuint32_t estr[3] = {1, 1, 1};
-      const CUtensorMapSwizzle swz = R == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : (R == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
-      CUresult r = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>((const void *)a.Hin), dims, strides, box,
-                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, row_tma_l2_promotion(),
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) for the row pass %d x %d x %lld", (int)r, a.ny, MX, nplanes);
-        return OX_ERR_CUDA;
-      }
-      auto k = fused_row_tma_kernel<T, MX, R, MODE>;
-      OX_TRY(set_smem(k, SMEM));
-      int grid = sm_count();   // one persistent CTA per SM
-      if ((long long)grid * 2 > ntiles) grid = (int)((ntiles + 1) / 2);
-      // (with a general 2-D window streamed from L2 the paired order measured 9% slower than single tiles: 2.29 vs 2.10 ms)
-      const bool general_window = a.window != nullptr && a.win_x == nullptr;
-      constexpr int G = 8 / R;   // row tiles per 128-byte line
-      a.tile_order = row_tma_tile_order((a.ny / R) % G == 0 && !general_window ? G : 0);
-      if ((a.ny / R) % G != 0 && a.tile_order >= 2) a.tile_order = 0;
-      if (a.tile_order >= 2) a.tile_order = G;
-      a.nplanes_fast = (int)nplanes;
-      k<<<grid, Cfg::NTHREADS, SMEM, g_stream>>>(a, tmap, (int)nplanes, (int)ntiles);
-      OX_KERNEL_CHECK();
-      *launched = true;
-    }
+    if (R == 2 && !row_tma_r2_enabled()) return OX_OK;
+    return launch_row_tma_cfg<T, MX, MODE, R, 2, 3>(a, nplanes, launched);
   }
   return OX_OK;
 }

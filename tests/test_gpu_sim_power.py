@@ -445,7 +445,7 @@ def test_tma_row_pass_matches_the_legacy_row_pass_and_the_oracle(pol, theory, mo
     taper = np.asarray(maps.get_taper(shape, wcs)[0])
     nsim = 5                                                     # 5 planes x 128 row tiles: odd tile counts per CTA
     out = {}
-    variants = ("tma", "tma_general_window", "w32", "w32_general_window")
+    variants = ("tma", "tma_general_window", "tma4", "tma4_general_window", "w32", "w32_general_window")
     for kb in ("legacy",) + variants:
         monkeypatch.setenv("ORPHX_KB", kb.split("_")[0])
         monkeypatch.setenv("ORPHX_WINDOW_SEPARABLE", "0" if "general" in kb else "1")
