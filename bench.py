@@ -685,7 +685,8 @@ def run_config_qe(cx, args, est, npix, dtype_name, nb, total_real, label, scalin
            "e2e": {"value": e2e_val, "unit": "realisations/s", "h2d_bytes_per_step": int(xin.array.nbytes * (2 if yin is not None else 1)),
                    "d2h_bytes_per_step": int(kout.array.nbytes),
                    "note": "qest.kappa_from_maps: observed maps from pinned host memory -> kappa maps in pinned host memory "
-                           "(+ mean-field accumulate on the device); PCIe-bound"},
+                           "(+ mean-field accumulate on the device); PCIe-bound: the call pipelines the realisations (upload of r+1 and "
+                           "download of r-1 on their own streams while r is reconstructed)"},
            "roofline": cx.roofline(st_ms, alg, f"QE_{est}{npix}_{dtype_name}"),
            "roofline_pipeline": {"algorithmic_bytes_per_realisation": pb, "achieved": value / cx.ws * pb / 1e9, "unit": "GB/s",
                                  "frac": value / cx.ws * pb / 1e9 / cx.peak,

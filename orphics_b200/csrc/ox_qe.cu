@@ -42,6 +42,19 @@ struct ox_qeplan {
   DevBuf tw, wxyT, wyT, normT, legT;
   int nlegs = 3;           // 3 (TT) or 6 (EB: real and imaginary parts of the spin-2 fields)
   DevBuf Hx, Hy, Kx, Ky, Lt, Pt, khT;
+  // host <-> device pipeline of ox_qe_reconstruct (host buffers, nbatch > 1): two staging slots, copy streams, events
+  DevBuf pipe_x[2], pipe_y[2], pipe_out[2];
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  ~ox_qeplan() {
+    for (int b = 0; b < 2; b++) {
+      if (ev_in[b]) cudaEventDestroy(ev_in[b]);
+      if (ev_c[b]) cudaEventDestroy(ev_c[b]);
+      if (ev_out[b]) cudaEventDestroy(ev_out[b]);
+    }
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
+  }
 };
 
 namespace {
@@ -885,6 +898,61 @@ int ox_qe_reconstruct(ox_qeplan *q, const void *x, const void *y, int where, int
   OX_REQUIRE(q && x && kappa_out, "ox_qe_reconstruct: null pointer");
   OX_REQUIRE(nbatch >= 1 && nbatch <= q->max_batch, "nbatch=%d outside 1..max_batch=%d", nbatch, q->max_batch);
   OX_REQUIRE(q->est != OX_QE_EB || (y && y != x), "EB needs the B leg");
+  {
+    // Host buffers, several realisations: one realisation at a time through two device staging slots, the upload of
+    // realisation r+1 and the download of realisation r-1 on their own (non-blocking) streams while realisation r is
+    // reconstructed on the library stream -- the call is PCIe-bound (2 x 134 MB per realisation at 4096^2 against
+    // 0.8 ms of kernels) and the two directions of the link run at the same time.  ORPHX_QE_PIPELINE=0: one batch, serial.
+    const char *env = getenv("ORPHX_QE_PIPELINE");
+    if (where == OX_HOST && out_where == OX_HOST && nbatch > 1 && !(env && env[0] == '0')) {
+      const size_t es = q->dtype == OX_F64 ? 8 : 4;
+      const size_t npix = (size_t)q->g->ny * q->g->nx;
+      const size_t in_bytes = (already_ft ? 2 : 1) * es * npix, out_bytes = (return_ft ? 2 : 1) * es * npix;
+      if (!q->s_h2d) {
+        OX_CUDA(cudaStreamCreateWithFlags(&q->s_h2d, cudaStreamNonBlocking));
+        OX_CUDA(cudaStreamCreateWithFlags(&q->s_d2h, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+          OX_CUDA(cudaEventCreateWithFlags(&q->ev_in[b], cudaEventDisableTiming));
+          OX_CUDA(cudaEventCreateWithFlags(&q->ev_c[b], cudaEventDisableTiming));
+          OX_CUDA(cudaEventCreateWithFlags(&q->ev_out[b], cudaEventDisableTiming));
+        }
+      }
+      for (int b = 0; b < 2; b++) {
+        OX_TRY(q->pipe_x[b].ensure(in_bytes));
+        if (y) OX_TRY(q->pipe_y[b].ensure(in_bytes));
+        OX_TRY(q->pipe_out[b].ensure(out_bytes));
+      }
+      OX_CUDA(cudaStreamSynchronize(g_stream));   // earlier work of the library stream may still use the buffers' memory
+      int st = OX_OK;
+      for (int r = 0; r < nbatch && st == OX_OK; r++) {
+        const int b = r & 1;
+        if (r >= 2) OX_CUDA(cudaStreamWaitEvent(q->s_h2d, q->ev_c[b], 0));      // slot b's previous realisation has been consumed
+        OX_CUDA(cudaMemcpyAsync(q->pipe_x[b].p, (const char *)x + (size_t)r * in_bytes, in_bytes, cudaMemcpyHostToDevice, q->s_h2d));
+        if (y) OX_CUDA(cudaMemcpyAsync(q->pipe_y[b].p, (const char *)y + (size_t)r * in_bytes, in_bytes, cudaMemcpyHostToDevice, q->s_h2d));
+        OX_CUDA(cudaEventRecord(q->ev_in[b], q->s_h2d));
+        OX_CUDA(cudaStreamWaitEvent(g_stream, q->ev_in[b], 0));
+        if (r >= 2) OX_CUDA(cudaStreamWaitEvent(g_stream, q->ev_out[b], 0));    // slot b's previous result has left
+        st = q->dtype == OX_F64
+                 ? reconstruct_T<double, double2>(q, q->pipe_x[b].p, y ? q->pipe_y[b].p : nullptr, OX_DEVICE, 1, already_ft, return_ft,
+                                                  accumulate_meanfield, q->pipe_out[b].p, OX_DEVICE)
+                 : reconstruct_T<float, float2>(q, q->pipe_x[b].p, y ? q->pipe_y[b].p : nullptr, OX_DEVICE, 1, already_ft, return_ft,
+                                                accumulate_meanfield, q->pipe_out[b].p, OX_DEVICE);
+        if (st != OX_OK) break;
+        OX_CUDA(cudaEventRecord(q->ev_c[b], g_stream));
+        OX_CUDA(cudaStreamWaitEvent(q->s_d2h, q->ev_c[b], 0));
+        OX_CUDA(cudaMemcpyAsync((char *)kappa_out + (size_t)r * out_bytes, q->pipe_out[b].p, out_bytes, cudaMemcpyDeviceToHost, q->s_d2h));
+        OX_CUDA(cudaEventRecord(q->ev_out[b], q->s_d2h));
+      }
+      cudaStreamSynchronize(q->s_h2d);
+      cudaStreamSynchronize(q->s_d2h);
+      OX_CUDA(cudaStreamSynchronize(g_stream));
+      if (st == OX_OK && accumulate_meanfield) {
+        add_count_kernel<<<1, 1, 0, g_stream>>>(q->mf_count(), (double)nbatch);
+        OX_KERNEL_CHECK();
+      }
+      return st;
+    }
+  }
   int st = q->dtype == OX_F64
                ? reconstruct_T<double, double2>(q, x, y, where, nbatch, already_ft, return_ft, accumulate_meanfield, kappa_out, out_where)
                : reconstruct_T<float, float2>(q, x, y, where, nbatch, already_ft, return_ft, accumulate_meanfield, kappa_out, out_where);
