@@ -167,6 +167,9 @@ class devmap(object):
             out = np.empty(self.shape, dtype=self.dtype)
             check(lib.ox_memcpy_d2h(ptr(out), C.c_void_p(self._ptr), out.nbytes))
             self._host = ndmap(out, self.wcs)
+        # read-only: writing into what np.asarray() hands out would change the host copy behind the device copy's back;
+        # item assignment on the devmap itself (which re-uploads) and np.array(m) (a copy) are the ways to edit
+        self._host.flags.writeable = False
         return self._host
 
     def __array__(self, dtype=None, copy=None):
@@ -199,7 +202,11 @@ class devmap(object):
 
     def __setitem__(self, idx, value):
         h = self.host()
-        h[idx] = value
+        h.flags.writeable = True
+        try:
+            h[idx] = value
+        finally:
+            h.flags.writeable = False
         self._dev_valid = False      # the host copy is now the newer one
         if self._owner is not None and self._ptr != self._owner.ptr:
             self._owner = None       # (a view: never write through into the parent's block)
@@ -302,14 +309,25 @@ class devmap(object):
                 return r
         outs = kwargs.get("out", ())
         if outs:
-            kwargs["out"] = tuple(o.host() if isinstance(o, devmap) else o for o in outs)
+            hosts = []
+            for o in outs:
+                if isinstance(o, devmap):
+                    h = o.host()
+                    h.flags.writeable = True
+                    hosts.append(h)
+                else:
+                    hosts.append(o)
+            kwargs["out"] = tuple(hosts)
         args = [x.host() if isinstance(x, devmap) else x for x in inputs]
-        res = getattr(ufunc, method)(*args, **kwargs)
-        for o in outs:
-            if isinstance(o, devmap):     # written on the host: the device copy is stale now
-                o._dev_valid = False
-                if o._owner is not None and o._ptr != o._owner.ptr:
-                    o._owner = None
+        try:
+            res = getattr(ufunc, method)(*args, **kwargs)
+        finally:
+            for o in outs:
+                if isinstance(o, devmap):     # written on the host: the device copy is stale now
+                    o._host.flags.writeable = False
+                    o._dev_valid = False
+                    if o._owner is not None and o._ptr != o._owner.ptr:
+                        o._owner = None
         return res
 
 

@@ -88,6 +88,12 @@ def test_devmap_behaves_as_the_ndmap_it_stands_for(setup):
     m3 = m.copy()
     np.multiply(h, 3.0, out=m3)
     assert np.array_equal(np.asarray(m3 * wd), (h * 3.0) * w)
+    # what np.asarray hands out is read-only (it is the cached host copy): editing goes through the devmap or a copy
+    with pytest.raises(ValueError):
+        np.asarray(m)[0, 0] = 1.0
+    c = np.array(m)
+    c[0, 0] = 1.0                                                         # np.array(m) is a private, writable copy
+    assert np.asarray(m)[0, 0] == h[0, 0]
     # from_host keeps a private copy: editing the caller's array afterwards reaches neither copy
     w2 = w.copy()
     d2 = enmap.devmap.from_host(w2)
