@@ -112,3 +112,27 @@ def test_views_item_assignment_and_read_only_host_copy(dm):
         m[3]
     with pytest.raises(TypeError):
         hash(m)
+
+
+def test_dense_theory_tables_reproduce_the_piecewise_linear_theory():
+    """Host half of the estimator's device set-up (lensing._dense_theory_tables): the dense integer-l tables interpolate
+    linearly to exactly what TheorySpectra.lCl / uCl return between the tabulated knots and above the last one; the first
+    knot is reported so that the caller can refuse geometries with modes below it; foreign theory objects are refused."""
+    from orphics_b200 import cosmology, lensing
+    th = cosmology.default_theory()
+    tabs, lo = lensing._dense_theory_tables(th, 21600.0)
+    assert lo == 2.0 and set(tabs) == {w + k for w in "lu" for k in ("TT", "EE", "BB", "TE")}
+    L = np.concatenate([np.linspace(2.0, 9500.0, 20011), [0.0, 8249.5, 8250.0, 8250.5, 12000.0]])
+    for which, f in (("l", th.lCl), ("u", th.uCl)):
+        for k in ("TT", "EE", "TE", "BB"):
+            t = tabs[which + k]
+            got = np.interp(L, np.arange(t.size, dtype=np.float64), t, left=0.0, right=0.0)
+            want = f(k, L)
+            assert np.max(np.abs(got - want)) <= 1e-15 * np.max(np.abs(want)) + 0.0, (which, k)
+
+    class Other:
+        def lCl(self, k, L):
+            return L * 0
+
+        uCl = lCl
+    assert lensing._dense_theory_tables(Other(), 3000.0) is None
