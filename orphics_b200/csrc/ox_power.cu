@@ -398,14 +398,23 @@ int ox_power2d(ox_powerplan *p, const void *maps1, const void *maps2, int where,
   size_t kbytes = 2 * es * (size_t)nbatch * p->ncomp * n;
   size_t pbytes = es * (size_t)nbatch * p->ncomp * p->ncomp * n;
   OX_TRY(forward_half(p, maps1, where, nbatch, nullptr, p->in1, p->kh1));
-  OX_TRY(p->full1.ensure(kbytes));
-  OX_TRY(expand(p, p->kh1.p, p->full1.p, nbatch, 1.0, flags));
-  const void *f2 = p->full1.p;
+  // device-resident outputs: the full-plane k-maps are expanded straight into the caller's buffers (no copy afterwards)
+  void *f1 = (out_where == OX_DEVICE && kmap1_out) ? kmap1_out : nullptr;
+  if (!f1) {
+    OX_TRY(p->full1.ensure(kbytes));
+    f1 = p->full1.p;
+  }
+  OX_TRY(expand(p, p->kh1.p, f1, nbatch, 1.0, flags));
+  const void *f2 = f1;
   if (maps2 && maps2 != maps1) {
     OX_TRY(forward_half(p, maps2, where, nbatch, nullptr, p->in2, p->kh2));
-    OX_TRY(p->full2.ensure(kbytes));
-    OX_TRY(expand(p, p->kh2.p, p->full2.p, nbatch, 1.0, flags));
-    f2 = p->full2.p;
+    void *g2 = (out_where == OX_DEVICE && kmap2_out) ? kmap2_out : nullptr;
+    if (!g2) {
+      OX_TRY(p->full2.ensure(kbytes));
+      g2 = p->full2.p;
+    }
+    OX_TRY(expand(p, p->kh2.p, g2, nbatch, 1.0, flags));
+    f2 = g2;
   }
   void *dst = p2d_out;
   if (out_where == OX_HOST) {
@@ -416,7 +425,7 @@ int ox_power2d(ox_powerplan *p, const void *maps1, const void *maps2, int where,
   int skip = (flags & OX_FLAG_SKIP_CROSS) ? 1 : 0;
   dim3 grid((unsigned)((n + PW_THREADS - 1) / PW_THREADS), nbatch);
 #define OX_LAUNCH(T2, T, NC)                                                                                   \
-  power2d_kernel<T2, T, NC><<<grid, PW_THREADS, 0, g_stream>>>((const T2 *)p->full1.p, (const T2 *)f2, n, norm, skip, (T *)dst)
+  power2d_kernel<T2, T, NC><<<grid, PW_THREADS, 0, g_stream>>>((const T2 *)f1, (const T2 *)f2, n, norm, skip, (T *)dst)
   if (p->dtype == OX_F64) {
     if (p->ncomp == 1) OX_LAUNCH(double2, double, 1);
     else if (p->ncomp == 2) OX_LAUNCH(double2, double, 2);
@@ -429,7 +438,7 @@ int ox_power2d(ox_powerplan *p, const void *maps1, const void *maps2, int where,
 #undef OX_LAUNCH
   OX_KERNEL_CHECK();
   if (out_where == OX_HOST) OX_TRY(stage_out(p2d_out, OX_HOST, dst, pbytes));
-  if (kmap1_out) OX_TRY(stage_out(kmap1_out, out_where, p->full1.p, kbytes));
+  if (kmap1_out) OX_TRY(stage_out(kmap1_out, out_where, f1, kbytes));      // (no-op when f1 already is the caller's buffer)
   if (kmap2_out) OX_TRY(stage_out(kmap2_out, out_where, f2, kbytes));
   return OX_OK;
 }
